@@ -1,0 +1,120 @@
+/*
+ * trico_b200_device.h - device-level C ABI of the B200 trico hot path.
+ *
+ * Plain C, plain pointers and sizes.  Everything here runs hand-written sm_100a kernels; there is
+ * no CPU fallback: every entry point returns 0 when CUDA is unavailable or a launch fails.
+ *
+ * This is the layer the archive API (trico_b200.h, the drop-in for the reference's
+ * trico/trico.h:36-94) is built on, and what bench.py times with device-resident buffers.
+ * Pointer arguments named d_* must be device pointers.
+ *
+ * Reference functions each entry point replaces are cited as /root/reference paths.
+ */
+#ifndef TRICO_B200_DEVICE_H
+#define TRICO_B200_DEVICE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef TB200_API
+#define TB200_API __attribute__((visibility("default")))
+#endif
+
+typedef struct tb200_ctx tb200_ctx;
+
+/* One context = one device + one CUDA stream + a workspace (look-back descriptors, tickets,
+ * legacy predictor tables).  `cuda_stream` may be NULL (the context creates its own stream) or an
+ * existing cudaStream_t (e.g. torch's current stream) so callers can time with their own events.
+ * Returns NULL if no CUDA device is usable. */
+TB200_API tb200_ctx* tb200_ctx_create(int device, void* cuda_stream);
+TB200_API void tb200_ctx_destroy(tb200_ctx* ctx);
+TB200_API void* tb200_ctx_stream(tb200_ctx* ctx);
+TB200_API int tb200_ctx_sync(tb200_ctx* ctx);                 /* 1 ok, 0 CUDA error */
+TB200_API const char* tb200_last_error(void);                /* text of the last failure in this thread */
+/* Number of kernels launched through this context so far (bench.py's gpu_launches). */
+TB200_API uint64_t tb200_ctx_launch_count(tb200_ctx* ctx);
+
+/* ---- v1 stream geometry (DESIGN.md "v1 wire format") ---- */
+#define TB200_V1_FIXED_BYTES 15u      /* u8 type, u32 count, u8 codec_info, u8 log2_chunk, u64 payload_bytes */
+/* codec of a stream type: 1 = FPC, 2 = LZ4 byte planes, 0 = not a stream type (trico.h:11-34) */
+TB200_API int tb200_stream_layout(int type, int* wordsize, int* ncomp, int* per_count);
+TB200_API uint64_t tb200_v1_nchunks(int type, uint32_t count, int log2_chunk);
+/* worst-case size of a whole v1 stream (fixed header + size table + payload) */
+TB200_API uint64_t tb200_v1_stream_bound(int type, uint32_t count, int log2_chunk);
+TB200_API int tb200_default_log2_chunk(int type, uint32_t count);
+
+/* ---- chunked FPC: replaces trico_transpose_*_aos_to_soa + trico_compress[_double_precision]
+ *      (trico/transpose_aos_to_soa.c:8-82, trico/floating_point_stream_compression.c:86,:576) ---- */
+/* d_in: AoS, n*ncomp words of `wordsize` bytes.  Writes u16 sizes[nchunks] and the packed chunk
+ * payloads; the payload byte count goes to d_total (aligned u64) and, little-endian, to the 8
+ * bytes at d_total_field (may be NULL).  Asynchronous on the context stream. */
+TB200_API int tb200_fpc_encode(tb200_ctx* ctx, int wordsize, int ncomp, const void* d_in, uint64_t n, int log2_chunk,
+                     int e1, int e2, uint8_t* d_sizes, uint8_t* d_payload, uint8_t* d_total_field, uint64_t* d_total);
+/* inverse: trico_decompress[_double_precision] + trico_transpose_*_soa_to_aos
+ * (floating_point_stream_compression.c:212,:803; transpose_aos_to_soa.c:18-82) */
+TB200_API int tb200_fpc_decode(tb200_ctx* ctx, int wordsize, int ncomp, const uint8_t* d_sizes, const uint8_t* d_payload,
+                     uint64_t payload_bytes, uint64_t n, int log2_chunk, int e1, int e2, void* d_out);
+
+/* ---- reference-format (v0) FPC streams, whole stream = one predictor chain ---- */
+/* Encodes `nstreams` component streams (component c = d_in[j*stride + c]) into slots of
+ * out_stride bytes at d_out; d_nbytes[c] receives each stream's length (5-byte header included).
+ * Byte-identical to trico_compress / trico_compress_double_precision. */
+TB200_API int tb200_fpc_encode_v0(tb200_ctx* ctx, int wordsize, const void* d_in, uint32_t n, uint32_t stride, int nstreams,
+                        int e1, int e2, uint8_t* d_out, uint64_t out_stride, uint32_t* d_nbytes);
+TB200_API uint64_t tb200_fpc_v0_bound(int wordsize, uint32_t n);
+/* Decodes `nstreams` v0 streams found at d_base + offsets[c] (host array of offsets);
+ * hash_info[c] = first byte of each stream (host knows it from the archive) selects table sizes.
+ * Element j of stream c goes to d_out[j*stride + c]. */
+TB200_API int tb200_fpc_decode_v0(tb200_ctx* ctx, int wordsize, const uint8_t* d_base, const uint64_t* offsets,
+                        const uint8_t* hash_info, int nstreams, uint32_t expect_n, void* d_out, uint32_t stride);
+
+/* ---- chunked byte-plane + LZ4: replaces trico_transpose_uint{16,32,64}_aos_to_soa +
+ *      LZ4_compress_default (transpose_aos_to_soa.c:84-147, lz4/lz4.c:1271) ---- */
+TB200_API int tb200_lz4_encode(tb200_ctx* ctx, int wordsize, const void* d_in, uint64_t n, int log2_chunk,
+                     uint8_t* d_sizes, uint8_t* d_payload, uint8_t* d_total_field, uint64_t* d_total);
+/* inverse: LZ4_decompress_safe (lz4/lz4.c:2078) + trico_transpose_uint*_soa_to_aos */
+TB200_API int tb200_lz4_decode(tb200_ctx* ctx, int wordsize, const uint8_t* d_sizes, const uint8_t* d_payload,
+                     uint64_t payload_bytes, uint64_t n, int log2_chunk, void* d_out);
+/* reference-format (v0) planes: `nplanes` whole-plane LZ4 blocks at d_base + offsets[p] of
+ * nbytes[p] compressed bytes, each decoding to n bytes; merged into n elements of nplanes bytes. */
+TB200_API int tb200_lz4_decode_v0(tb200_ctx* ctx, int nplanes, const uint8_t* d_base, const uint64_t* offsets,
+                        const uint32_t* nbytes, uint64_t n, void* d_out);
+
+/* ---- whole streams ---- */
+/* Encodes one v1 stream (header + size table + payload, assembled in-kernel) into d_out.
+ * The stream's total byte count is written to *d_stream_bytes (device u64).  `count` is the value
+ * stored in the stream header (trico.c:221). */
+TB200_API int tb200_encode_stream(tb200_ctx* ctx, int type, const void* d_data, uint32_t count, int log2_chunk,
+                        uint8_t* d_out, uint64_t out_cap, uint64_t* d_stream_bytes);
+/* Decodes one v1 stream whose 15 header bytes are given in host memory (`header`) and whose full
+ * bytes (starting at the type byte) are on the device at d_stream. */
+TB200_API int tb200_decode_stream(tb200_ctx* ctx, const uint8_t* header, const uint8_t* d_stream, uint64_t stream_bytes, void* d_out);
+
+/* ---- standalone transposes (the 14 exported trico_transpose_* symbols) ---- */
+TB200_API int tb200_deinterleave(tb200_ctx* ctx, int wordsize, int ncomp, const void* d_aos, uint64_t n, void* const* d_comp);
+TB200_API int tb200_interleave(tb200_ctx* ctx, int wordsize, int ncomp, void* d_aos, uint64_t n, const void* const* d_comp);
+
+/* ---- memory helpers (thin wrappers so C / ctypes callers need no CUDA headers) ---- */
+TB200_API void* tb200_device_alloc(uint64_t bytes);
+TB200_API void tb200_device_free(void* d);
+TB200_API void* tb200_host_alloc_pinned(uint64_t bytes);
+TB200_API void tb200_host_free_pinned(void* h);
+TB200_API int tb200_memcpy_h2d(tb200_ctx* ctx, void* d, const void* h, uint64_t bytes);   /* async on ctx stream */
+TB200_API int tb200_memcpy_d2h(tb200_ctx* ctx, void* h, const void* d, uint64_t bytes);   /* async on ctx stream */
+TB200_API int tb200_device_count(void);
+/* 1 if p points to device (or managed) memory, 0 for ordinary / pinned host memory */
+TB200_API int tb200_pointer_is_device(const void* p);
+/* timing on the context stream: event handles are opaque */
+TB200_API void* tb200_event_create(void);
+TB200_API void tb200_event_destroy(void* ev);
+TB200_API int tb200_event_record(tb200_ctx* ctx, void* ev);
+TB200_API float tb200_event_elapsed_ms(void* start, void* stop);   /* synchronises on `stop` */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,352 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI, against the CPU oracle, the
+reference-generated golden fixtures and (when its prebuilt .so travelled along) the compiled
+reference itself.  Bit-exact everywhere: this path is integer/byte work only.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FPC_TYPES = [1, 2, 5, 6, 7, 8, 9, 10, 11, 12, 15, 16]
+LZ4_TYPES = [3, 4, 13, 14, 17, 18, 19, 20]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from trico_b200 import Device
+    d = Device(0)
+    yield d
+    d.close()
+
+
+@pytest.fixture(scope="module")
+def ours():
+    """our drop-in library behind the same ctypes binding the reference is driven through"""
+    from checkers import TricoCApi
+    import trico_b200
+    trico_b200.load()
+    return TricoCApi(trico_b200.LIB_PATH)
+
+
+def _fromhex(h, dtype):
+    return np.frombuffer(bytes.fromhex(h), dtype)
+
+
+def _stream_input(golden, ty):
+    b = golden["bunny"]
+    if ty in (6, 8):
+        return b["in_6"].reshape(-1), int(b["cnt_6"])
+    return b[f"in_{ty}"].reshape(-1), int(b[f"cnt_{ty}"]) * (3 if ty == 7 else 1)
+
+
+def _synthetic(ty, n, seed):
+    """n = stored count; returns flat array of the stream's scalars"""
+    from trico_b200 import STREAM_DTYPES
+    rng = np.random.default_rng(seed)
+    dt = np.dtype(STREAM_DTYPES[ty])
+    arity = {1: 3, 2: 3, 5: 2, 6: 2, 7: 2, 8: 2, 9: 3, 10: 3, 11: 3, 12: 3, 3: 3, 4: 3}.get(ty, 1)
+    m = n * arity
+    if dt.kind == "f":
+        walk = np.cumsum(rng.standard_normal(m) * 0.01) + rng.choice([-3.0, 0.5, 100.0])
+        return walk.astype(dt)
+    if ty in (3, 4):
+        base = np.repeat(np.arange(n), 3) + rng.integers(0, 50, m)
+        return base.astype(dt)
+    hi = min(2 ** (8 * dt.itemsize) - 1, 2 ** 40)
+    return (rng.integers(0, hi, m, dtype=np.uint64) >> np.uint64(rng.integers(0, 8))).astype(dt)
+
+
+# ------------------------------------------------------------------------------- chunked FPC
+@pytest.mark.parametrize("ty", FPC_TYPES)
+def test_fpc_chunk_bytes_match_oracle(dev, oracle, golden, ty):
+    """every chunk payload is the reference stream format: the GPU stream must equal the oracle's
+    v1 stream byte for byte (chunk = reference FPC stream minus its 5-byte header)"""
+    data, cnt = _stream_input(golden, ty)
+    for log2c in (5, 7, 9):
+        got = dev.encode_stream(ty, data, cnt, log2c)
+        want = oracle.v1_write_stream(ty, data, cnt, log2c, 2, 4)
+        assert got == want, (ty, log2c)
+        back = dev.decode_stream(got)
+        assert back.tobytes() == data.tobytes()
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1000, 12289, 100003])
+def test_fpc_ragged_sizes(dev, oracle, n):
+    for ty in (1, 2, 5, 16, 15):
+        data = _synthetic(ty, n, n)
+        got = dev.encode_stream(ty, data, n)
+        log2c = got[6]
+        assert got == oracle.v1_write_stream(ty, data, n, log2c, 2, 4), (ty, n)
+        assert dev.decode_stream(got).tobytes() == data.tobytes()
+
+
+def test_fpc_special_values(dev, oracle):
+    f = np.array([0.0, -0.0, np.nan, np.inf, -np.inf, 1e-45, -1e-45, 3.4e38, 1.17549435e-38] * 50, np.float32)
+    rng = np.random.default_rng(3)
+    noise32 = rng.integers(0, 2**32, 3 * 4099, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    noise64 = rng.integers(0, 2**63, 3 * 1031, dtype=np.uint64).view(np.float64)
+    for ty, data in ((1, f[:447]), (15, f), (1, noise32), (2, noise64), (1, np.zeros(3000, np.float32))):
+        cnt = data.size // dev.layout(ty)["ncomp"]
+        got = dev.encode_stream(ty, data, cnt)
+        assert got == oracle.v1_write_stream(ty, data, cnt, got[6], 2, 4)
+        assert dev.decode_stream(got).tobytes() == data.tobytes()
+
+
+def test_fpc_decode_of_oracle_streams(dev, oracle):
+    """the GPU decoder on streams the CPU oracle wrote, including other exponent pairs"""
+    for ty in (1, 2, 5, 15):
+        data = _synthetic(ty, 5000, 11)
+        for (e1, e2) in ((2, 4), (4, 4), (2, 2), (4, 6), (6, 8)):
+            for log2c in (6, 9):
+                s = oracle.v1_write_stream(ty, data, 5000, log2c, e1, e2)
+                assert dev.decode_stream(s).tobytes() == data.tobytes(), (ty, e1, e2, log2c)
+
+
+# ------------------------------------------------------------------------- chunked planes+LZ4
+@pytest.mark.parametrize("ty", LZ4_TYPES)
+def test_lz4_streams_valid_and_roundtrip(dev, oracle, golden, ty):
+    data, cnt = _stream_input(golden, ty)
+    for log2c in (8, 12, 14, 15):
+        s = dev.encode_stream(ty, data, cnt, log2c)
+        # container + every block parse with the CPU oracle
+        t, c, arr, used = oracle.v1_read_stream(b"Trco\x01\0\0\0" + s, 8)
+        assert (t, c, used) == (ty, cnt, len(s))
+        assert arr.tobytes() == data.tobytes()
+        # every block honours the LZ4 end-of-block rules (lz4.c:189-196)
+        lay = oracle.layout(ty)
+        n = cnt * lay["per_count"]
+        B = 1 << log2c
+        nr = (n + B - 1) // B
+        nch = nr * lay["wordsize"]
+        sizes = np.frombuffer(s[15:15 + 2 * nch], np.uint16)
+        off = 15 + 2 * nch
+        for k in range(nr):
+            raw = min(B, n - k * B)
+            for p in range(lay["wordsize"]):
+                nb = int(sizes[k * lay["wordsize"] + p])
+                assert oracle.lz4_validate(s[off:off + nb], raw) == raw
+                off += nb
+        assert off == len(s)
+        assert dev.decode_stream(s).tobytes() == data.tobytes()
+
+
+@pytest.mark.parametrize("n", [1, 3, 12, 13, 100, 4096, 16384, 16385, 70001, 300007])
+def test_lz4_ragged_sizes(dev, oracle, n):
+    for ty in (3, 13, 17, 18, 20):
+        data = _synthetic(ty, n, n + 1)
+        s = dev.encode_stream(ty, data, n)
+        _, _, arr, _ = oracle.v1_read_stream(b"Trco\x01\0\0\0" + s, 8)
+        assert arr.tobytes() == data.tobytes(), (ty, n)
+        assert dev.decode_stream(s).tobytes() == data.tobytes(), (ty, n)
+
+
+def test_lz4_decode_of_oracle_streams(dev, oracle):
+    rng = np.random.default_rng(8)
+    cases = {
+        3: np.repeat(np.arange(20000, dtype=np.uint32), 3) + rng.integers(0, 3, 60000).astype(np.uint32),
+        17: rng.integers(0, 4, 50000).astype(np.uint8),
+        18: (np.arange(70000) // 7).astype(np.uint16),
+        20: rng.integers(0, 2**20, 30000, dtype=np.uint64),
+        13: np.full(100000, 0xFF102030, np.uint32),
+    }
+    for ty, data in cases.items():
+        cnt = data.size // (3 if ty == 3 else 1)
+        for log2c in (10, 14):
+            s = oracle.v1_write_stream(ty, data, cnt, log2c)
+            assert dev.decode_stream(s).tobytes() == data.tobytes(), (ty, log2c)
+
+
+def test_lz4_ratio_close_to_reference(dev, ref, oracle, golden):
+    """same block size, GPU matcher vs the reference's LZ4_compress_default"""
+    data, cnt = _stream_input(golden, 3)
+    s = dev.encode_stream(3, data, cnt, 14)
+    planes = oracle.planes_split(data)
+    B, n = 1 << 14, data.size
+    ref_total = sum(len(ref.lz4_compress(planes[p, k:k + B].tobytes())) for p in range(4) for k in range(0, n, B))
+    ours_total = len(s) - 15 - 2 * 4 * ((n + B - 1) // B)
+    assert ours_total <= ref_total * 1.05, (ours_total, ref_total)
+
+
+# ------------------------------------------------------------------- archive API, all types
+def test_archive_roundtrip_all_types(ours, oracle, golden):
+    streams = []
+    for ty in range(1, 21):
+        data, cnt = _stream_input(golden, ty)
+        streams.append((ty, data, cnt // 3 if ty == 7 else cnt))
+    blob = ours.encode(streams)
+    assert blob[:4] == b"Trco" and int.from_bytes(blob[4:8], "little") == 1
+    # the CPU oracle understands the archive
+    version, dec = oracle.read_archive(blob)
+    assert version == 1 and [d[0] for d in dec] == list(range(1, 21))
+    for (ty, cnt, arr) in dec:
+        assert arr.tobytes() == _stream_input(golden, ty)[0].tobytes(), ty
+    # and so does our own reader
+    version, dec2 = ours.decode(blob, oracle)
+    assert version == 1
+    for (ty, cnt, arr) in dec2:
+        want, wcnt = _stream_input(golden, ty)
+        assert cnt == wcnt and arr.tobytes() == want.tobytes(), ty
+
+
+def test_empty_archive_and_errors(ours):
+    L = ours.lib
+    a = L.trico_open_archive_for_writing(1024)
+    assert L.trico_get_size(a) == 8
+    blob = C.string_at(L.trico_get_buffer_pointer(a), 8)
+    L.trico_close_archive(a)
+    assert blob == b"Trco\0\0\0\0"                      # trico.tests test_header: version 0, 8 bytes
+    buf = np.frombuffer(blob, np.uint8)
+    r = L.trico_open_archive_for_reading(buf.ctypes.data_as(C.c_void_p), 8)
+    assert r and L.trico_get_version(r) == 0 and L.trico_get_next_stream_type(r) == 0
+    assert L.trico_skip_next_stream(r) == 1
+    p = C.c_void_p(0)
+    assert L.trico_read_vertices(r, C.byref(p)) == 0    # wrong stream type -> 0 (trico.c:946)
+    assert L.trico_get_number_of_vertices(r) == 0
+    L.trico_close_archive(r)
+    bad = np.frombuffer(b"Nope\0\0\0\0", np.uint8)
+    assert not L.trico_open_archive_for_reading(bad.ctypes.data_as(C.c_void_p), 8)   # trico.c:116
+
+
+def test_skip_and_truncation(ours, oracle, golden):
+    v, cv = _stream_input(golden, 1)
+    t, ct = _stream_input(golden, 3)
+    blob = ours.encode([(1, v, cv), (3, t, ct), (15, v[:100], 100)])
+    L = ours.lib
+    buf = np.frombuffer(blob, np.uint8)
+    r = L.trico_open_archive_for_reading(buf.ctypes.data_as(C.c_void_p), len(blob))
+    assert L.trico_get_next_stream_type(r) == 1 and L.trico_get_number_of_vertices(r) == cv
+    assert L.trico_skip_next_stream(r) == 1
+    assert L.trico_get_next_stream_type(r) == 3 and L.trico_get_number_of_triangles(r) == ct
+    out = np.zeros(ct * 3, np.uint32)
+    p = C.c_void_p(out.ctypes.data)
+    assert L.trico_read_triangles(r, C.byref(p)) == 1 and out.tobytes() == t.tobytes()
+    assert L.trico_get_next_stream_type(r) == 15
+    assert L.trico_skip_next_stream(r) == 1 and L.trico_get_next_stream_type(r) == 0
+    L.trico_close_archive(r)
+    cut = np.frombuffer(blob[:len(blob) // 2], np.uint8)
+    r = L.trico_open_archive_for_reading(cut.ctypes.data_as(C.c_void_p), cut.size)
+    outv = np.zeros(cv * 3, np.float32)
+    p = C.c_void_p(outv.ctypes.data)
+    ok1 = L.trico_read_vertices(r, C.byref(p))
+    ok2 = L.trico_skip_next_stream(r) if ok1 else 0
+    assert not (ok1 and ok2)                            # truncated data -> 0 (trico.c:71)
+    L.trico_close_archive(r)
+
+
+# --------------------------------------------------------------- reference-format (v0) input
+def test_legacy_archives_from_reference(ours, oracle, golden):
+    """archives written by the unmodified reference decode bit-exactly on the GPU"""
+    b = golden["bunny"]
+    for ty in range(1, 21):
+        if ty in (6, 8):
+            continue
+        blob = b[f"v0_{ty}"].tobytes()
+        version, dec = ours.decode(blob, oracle)
+        assert version == 0 and len(dec) == 1
+        want, wcnt = _stream_input(golden, ty)
+        assert dec[0][0] == ty and dec[0][1] == wcnt
+        assert dec[0][2].tobytes() == want.tobytes(), ty
+    version, dec = ours.decode(b["v0_multi"].tobytes(), oracle)
+    assert [d[0] for d in dec] == [1, 3, 9, 13]
+    assert dec[0][2].tobytes() == b["vertices"].tobytes() and dec[1][2].tobytes() == b["triangles"].tobytes()
+
+
+def test_legacy_double_uv_payload(ours, oracle, golden):
+    # the reference tags its double-uv stream 5 (trico.c:622); with the tag corrected to 6 the GPU
+    # legacy path decodes the reference's payload bit-exactly
+    blob = golden["bunny"]["v0_6_as_written_by_reference"].tobytes()
+    fixed = blob[:8] + bytes([6]) + blob[9:]
+    _, dec = ours.decode(fixed, oracle)
+    assert dec[0][2].tobytes() == golden["bunny"]["in_6"].tobytes()
+
+
+# ------------------------------------------------------------------------------ raw codec API
+def test_raw_codec_byte_identical_to_reference(ours, golden):
+    """trico_compress / trico_decompress on the GPU reproduce the reference's bytes (KAT vectors)"""
+    for key, dt, w in (("fpc32", np.uint32, 4), ("fpc64", np.uint64, 8)):
+        for case in golden["kat"][key]:
+            vals = _fromhex(case["in"], dt)
+            if vals.size > 300 and case["e1"] > 10:
+                continue
+            want = bytes.fromhex(case["out"])
+            fvals = vals.view(np.float32 if w == 4 else np.float64)
+            assert ours.compress(fvals, case["e1"], case["e2"]) == want, (key, case["e1"], case["e2"], vals.size)
+            assert np.array_equal(ours.decompress(want, w), vals)
+
+
+def test_raw_codec_side_by_side(ours, ref):
+    rng = np.random.default_rng(12)
+    for n in (1, 9, 1000, 34834):
+        walk = (np.cumsum(rng.standard_normal(n) * 0.001) - 0.05).astype(np.float32)
+        s = ref.compress(walk, 4, 10)
+        assert ours.compress(walk, 4, 10) == s
+        assert np.array_equal(ours.decompress(s, 4), ref.decompress(s, 4))
+        d = walk.astype(np.float64)
+        s = ref.compress(d, 20, 20)
+        assert ours.compress(d, 20, 20) == s
+        assert np.array_equal(ours.decompress(s, 8), ref.decompress(s, 8))
+
+
+# --------------------------------------------------------------------------------- transposes
+def test_transposes(ours, oracle):
+    L = ours.lib
+    rng = np.random.default_rng(4)
+    n = 10007
+    v = rng.standard_normal(n * 3).astype(np.float32)
+    x, y, z = (np.zeros(n, np.float32) for _ in range(3))
+    px, py, pz = (C.c_void_p(a.ctypes.data) for a in (x, y, z))
+    L.trico_transpose_xyz_aos_to_soa(C.byref(px), C.byref(py), C.byref(pz), C.c_void_p(v.ctypes.data), C.c_uint32(n))
+    assert np.array_equal(x, v[0::3]) and np.array_equal(y, v[1::3]) and np.array_equal(z, v[2::3])
+    back = np.zeros(n * 3, np.float32)
+    pb = C.c_void_p(back.ctypes.data)
+    L.trico_transpose_xyz_soa_to_aos(C.byref(pb), px, py, pz, C.c_uint32(n))
+    assert np.array_equal(back, v)
+    idx = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    planes = [np.zeros(n, np.uint8) for _ in range(4)]
+    pp = [C.c_void_p(p.ctypes.data) for p in planes]
+    L.trico_transpose_uint32_aos_to_soa(C.byref(pp[0]), C.byref(pp[1]), C.byref(pp[2]), C.byref(pp[3]), C.c_void_p(idx.ctypes.data), C.c_uint32(n))
+    want = oracle.planes_split(idx)
+    for k in range(4):
+        assert np.array_equal(planes[k], want[k])
+    out = np.zeros(n, np.uint32)
+    po = C.c_void_p(out.ctypes.data)
+    L.trico_transpose_uint32_soa_to_aos(C.byref(po), pp[0], pp[1], pp[2], pp[3], C.c_uint32(n))
+    assert np.array_equal(out, idx)
+    d = rng.standard_normal(n * 2)
+    u, w = np.zeros(n), np.zeros(n)
+    pu, pw = C.c_void_p(u.ctypes.data), C.c_void_p(w.ctypes.data)
+    L.trico_transpose_uv_aos_to_soa_double_precision(C.byref(pu), C.byref(pw), C.c_void_p(d.ctypes.data), C.c_uint32(n))
+    assert np.array_equal(u, d[0::2]) and np.array_equal(w, d[1::2])
+    q = rng.integers(0, 2**63, n, dtype=np.uint64)
+    p8 = [np.zeros(n, np.uint8) for _ in range(8)]
+    pp8 = [C.c_void_p(p.ctypes.data) for p in p8]
+    L.trico_transpose_uint64_aos_to_soa(*[C.byref(p) for p in pp8], C.c_void_p(q.ctypes.data), C.c_uint32(n))
+    want = oracle.planes_split(q)
+    for k in range(8):
+        assert np.array_equal(p8[k], want[k])
+
+
+# ----------------------------------------------------------------------- bigger, by property
+def test_medium_mesh_roundtrip_properties(dev, oracle):
+    """a 2M-vertex synthetic mesh: round trip exact, a sample of chunks byte-identical to the oracle"""
+    from trico_b200.synth import grid_mesh
+    v, t = grid_mesh(1500, 1400, jitter=1.0, seed=7)
+    nv, nt = v.shape[0], t.shape[0]
+    s = dev.encode_stream(1, v.reshape(-1), nv)
+    assert dev.decode_stream(s).tobytes() == v.tobytes()
+    # chunks 0..255 against the oracle (prefix of the stream is independent of the rest)
+    S = 1 << s[6]
+    head_n = 256 * S
+    so = oracle.v1_write_stream(1, v[:head_n].reshape(-1), head_n, s[6], 2, 4)
+    nch_full = 3 * ((nv + S - 1) // S)
+    sizes_full = np.frombuffer(s[15:15 + 2 * nch_full], np.uint16)
+    sizes_head = np.frombuffer(so[15:15 + 2 * 3 * 256], np.uint16)
+    assert np.array_equal(sizes_full[:3 * 256], sizes_head)
+    nb = int(sizes_head.sum())
+    assert s[15 + 2 * nch_full:15 + 2 * nch_full + nb] == so[15 + 2 * 3 * 256:15 + 2 * 3 * 256 + nb]
+    s3 = dev.encode_stream(3, t.reshape(-1), nt)
+    assert dev.decode_stream(s3).tobytes() == t.tobytes()
+    ratio = (v.nbytes + t.nbytes) / (len(s) + len(s3))
+    assert ratio > 2.0

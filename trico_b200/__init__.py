@@ -1,0 +1,203 @@
+"""trico_b200 - B200-native encode/decode hot path of the trico mesh-compression library.
+
+The product is ``trico_b200/lib/libtrico_b200.so``: host C (csrc/archive.c) exporting the
+reference's C API plus a device-level C ABI (include/trico_b200_device.h), over hand-written
+sm_100a CUDA kernels (csrc/*.cuh).  This Python package is only a loader and a thin ctypes mirror
+used by the tests and bench.py; it contains no codec logic and no CPU fallback - if the library
+cannot be loaded, or no CUDA device is present, calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB as LIB_PATH
+from .build import build as build_library
+
+__all__ = ["LIB_PATH", "build_library", "load", "Device", "STREAM_DTYPES", "TB200Error"]
+
+_vp = C.c_void_p
+_lib = None
+
+
+class TB200Error(RuntimeError):
+    pass
+
+
+# scalar dtype per stream type (trico/trico.h:11-34)
+STREAM_DTYPES = {1: np.float32, 2: np.float64, 3: np.uint32, 4: np.uint64, 5: np.float32, 6: np.float64,
+                 7: np.float32, 8: np.float64, 9: np.float32, 10: np.float64, 11: np.float32, 12: np.float64,
+                 13: np.uint32, 14: np.uint32, 15: np.float32, 16: np.float64, 17: np.uint8, 18: np.uint16,
+                 19: np.uint32, 20: np.uint64}
+
+
+def load() -> C.CDLL:
+    """Load libtrico_b200.so (building it in-tree first if it is missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build_library()
+    L = C.CDLL(LIB_PATH)
+    sig = {
+        "tb200_ctx_create": (_vp, [C.c_int, _vp]),
+        "tb200_ctx_destroy": (None, [_vp]),
+        "tb200_ctx_stream": (_vp, [_vp]),
+        "tb200_ctx_sync": (C.c_int, [_vp]),
+        "tb200_last_error": (C.c_char_p, []),
+        "tb200_ctx_launch_count": (C.c_uint64, [_vp]),
+        "tb200_stream_layout": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "tb200_v1_nchunks": (C.c_uint64, [C.c_int, C.c_uint32, C.c_int]),
+        "tb200_v1_stream_bound": (C.c_uint64, [C.c_int, C.c_uint32, C.c_int]),
+        "tb200_default_log2_chunk": (C.c_int, [C.c_int, C.c_uint32]),
+        "tb200_fpc_encode": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_uint64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+        "tb200_fpc_decode": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, _vp]),
+        "tb200_fpc_encode_v0": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, _vp]),
+        "tb200_fpc_v0_bound": (C.c_uint64, [C.c_int, C.c_uint32]),
+        "tb200_fpc_decode_v0": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_uint32, _vp, C.c_uint32]),
+        "tb200_lz4_encode": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp, _vp]),
+        "tb200_lz4_decode": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_uint64, C.c_uint64, C.c_int, _vp]),
+        "tb200_lz4_decode_v0": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint64, _vp]),
+        "tb200_encode_stream": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, C.c_int, _vp, C.c_uint64, _vp]),
+        "tb200_decode_stream": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
+        "tb200_deinterleave": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_uint64, _vp]),
+        "tb200_interleave": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_uint64, _vp]),
+        "tb200_device_alloc": (_vp, [C.c_uint64]),
+        "tb200_device_free": (None, [_vp]),
+        "tb200_host_alloc_pinned": (_vp, [C.c_uint64]),
+        "tb200_host_free_pinned": (None, [_vp]),
+        "tb200_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
+        "tb200_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
+        "tb200_device_count": (C.c_int, []),
+        "tb200_pointer_is_device": (C.c_int, [_vp]),
+        "tb200_event_create": (_vp, []),
+        "tb200_event_destroy": (None, [_vp]),
+        "tb200_event_record": (C.c_int, [_vp, _vp]),
+        "tb200_event_elapsed_ms": (C.c_float, [_vp, _vp]),
+        "trico_b200_last_error": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+class DeviceBuffer:
+    """A cudaMalloc'd buffer owned by Python."""
+
+    def __init__(self, lib, nbytes: int):
+        self._lib = lib
+        self.nbytes = int(nbytes)
+        self.ptr = lib.tb200_device_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise TB200Error(lib.tb200_last_error().decode())
+
+    def free(self):
+        if self.ptr:
+            self._lib.tb200_device_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Device:
+    """ctypes mirror of the device-level C ABI on one GPU (one context = one CUDA stream)."""
+
+    def __init__(self, index: int = 0, cuda_stream: int | None = None):
+        self.lib = load()
+        self.ctx = self.lib.tb200_ctx_create(index, _vp(cuda_stream) if cuda_stream else None)
+        if not self.ctx:
+            raise TB200Error("no usable CUDA device (trico_b200 has no CPU fallback): " + self.lib.tb200_last_error().decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.tb200_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _ck(self, ok):
+        if not ok:
+            raise TB200Error(self.lib.tb200_last_error().decode())
+
+    def sync(self):
+        self._ck(self.lib.tb200_ctx_sync(self.ctx))
+
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self.lib, nbytes)
+
+    def upload(self, arr) -> DeviceBuffer:
+        arr = np.ascontiguousarray(arr)
+        buf = self.alloc(arr.nbytes + 64)
+        if arr.nbytes:
+            self._ck(self.lib.tb200_memcpy_h2d(self.ctx, buf.ptr, arr.ctypes.data_as(_vp), arr.nbytes))
+            self.sync()
+        return buf
+
+    def download(self, ptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, np.uint8)
+        if nbytes:
+            self._ck(self.lib.tb200_memcpy_d2h(self.ctx, out.ctypes.data_as(_vp), _vp(ptr), nbytes))
+            self.sync()
+        return out
+
+    @property
+    def launches(self) -> int:
+        return self.lib.tb200_ctx_launch_count(self.ctx)
+
+    def layout(self, stream_type: int):
+        w, nc, pc = C.c_int(0), C.c_int(0), C.c_int(0)
+        codec = self.lib.tb200_stream_layout(stream_type, C.byref(w), C.byref(nc), C.byref(pc))
+        return dict(codec=codec, wordsize=w.value, ncomp=nc.value, per_count=pc.value)
+
+    # -- whole v1 streams (device resident) ------------------------------------------------
+    def encode_stream_device(self, stream_type: int, d_data: int, count: int, d_out: int, out_cap: int, d_bytes: int, log2_chunk: int = 0):
+        self._ck(self.lib.tb200_encode_stream(self.ctx, stream_type, _vp(d_data), count, log2_chunk, _vp(d_out), out_cap, _vp(d_bytes)))
+
+    def decode_stream_device(self, header: bytes, d_stream: int, stream_bytes: int, d_out: int):
+        hb = (C.c_uint8 * 15).from_buffer_copy(header[:15])
+        self._ck(self.lib.tb200_decode_stream(self.ctx, hb, _vp(d_stream), stream_bytes, _vp(d_out)))
+
+    def encode_stream(self, stream_type: int, data, count: int, log2_chunk: int = 0) -> bytes:
+        """host array -> v1 stream bytes (type byte first)."""
+        data = np.ascontiguousarray(data, dtype=STREAM_DTYPES[stream_type])
+        if log2_chunk <= 0:
+            log2_chunk = self.lib.tb200_default_log2_chunk(stream_type, count)
+        bound = self.lib.tb200_v1_stream_bound(stream_type, count, log2_chunk)
+        d_in = self.upload(data)
+        d_out = self.alloc(bound)
+        d_sz = self.alloc(64)
+        self.encode_stream_device(stream_type, d_in.ptr, count, d_out.ptr, bound, d_sz.ptr, log2_chunk)
+        nbytes = int(self.download(d_sz.ptr, 8).view(np.uint64)[0])
+        out = self.download(d_out.ptr, nbytes).tobytes()
+        for b in (d_in, d_out, d_sz):
+            b.free()
+        return out
+
+    def decode_stream(self, stream: bytes) -> np.ndarray:
+        """v1 stream bytes -> flat host array of the stream's scalars."""
+        stream_type = stream[0]
+        count = int.from_bytes(stream[1:5], "little")
+        lay = self.layout(stream_type)
+        nsc = count * lay["per_count"] * (lay["ncomp"] if lay["codec"] == 1 else 1)
+        dtype = np.dtype(STREAM_DTYPES[stream_type])
+        d_s = self.upload(np.frombuffer(stream, np.uint8))
+        d_o = self.alloc(nsc * dtype.itemsize + 64)
+        self.decode_stream_device(stream, d_s.ptr, len(stream), d_o.ptr)
+        out = self.download(d_o.ptr, nsc * dtype.itemsize).view(dtype)
+        d_s.free()
+        d_o.free()
+        return out

@@ -1,0 +1,361 @@
+// device_api.cu - thin extern "C" layer over the sm_100a kernels (include/trico_b200_device.h).
+// Owns the CUDA stream, the per-context workspace and every kernel launch.  No CPU fallback.
+#include "../../include/trico_b200_device.h"
+
+#include "common.cuh"
+#include "fpc.cuh"
+#include "lz4.cuh"
+#include "planes.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+using namespace tb200;
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char* what, cudaError_t e)
+  {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+  }
+static int fail_msg(const char* what)
+  {
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return 0;
+  }
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(#call, e__); } while (0)
+
+extern "C" const char* tb200_last_error(void) { return g_err; }
+
+struct tb200_ctx
+  {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  uint8_t* ws;            // zeroed-per-launch scratch: [ticket (16 B) | descriptors]
+  size_t ws_bytes;
+  uint8_t* big;           // large scratch (legacy tables, plane buffers)
+  size_t big_bytes;
+  uint64_t launches;
+  int max_smem_optin;
+  };
+
+extern "C" int tb200_device_count(void)
+  {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+  }
+
+extern "C" tb200_ctx* tb200_ctx_create(int device, void* cuda_stream)
+  {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { fail("cudaGetDeviceCount (no CUDA device: the B200 path has no CPU fallback)", e); return nullptr; }
+  if (device < 0 || device >= n) { fail_msg("tb200_ctx_create: bad device index"); return nullptr; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { fail("cudaSetDevice", e); return nullptr; }
+  tb200_ctx* c = (tb200_ctx*)calloc(1, sizeof(tb200_ctx));
+  c->device = device;
+  if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+  else
+    {
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail("cudaStreamCreate", e); free(c); return nullptr; }
+    c->own_stream = true;
+    }
+  cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  return c;
+  }
+
+extern "C" void tb200_ctx_destroy(tb200_ctx* c)
+  {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->ws) cudaFree(c->ws);
+  if (c->big) cudaFree(c->big);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  free(c);
+  }
+
+extern "C" void* tb200_ctx_stream(tb200_ctx* c) { return (void*)c->stream; }
+extern "C" uint64_t tb200_ctx_launch_count(tb200_ctx* c) { return c->launches; }
+
+extern "C" int tb200_ctx_sync(tb200_ctx* c)
+  {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return 1;
+  }
+
+// workspace for one launch: 16-byte ticket block followed by `ntiles` 64-bit descriptors, zeroed.
+static int ws_prepare(tb200_ctx* c, uint64_t ntiles, uint32_t** ticket, uint64_t** desc)
+  {
+  const size_t need = 16 + (size_t)ntiles * 8;
+  if (need > c->ws_bytes)
+    {
+    // the previous buffer may still be in use by queued kernels
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->ws) CK(cudaFree(c->ws));
+    c->ws = nullptr; c->ws_bytes = 0;
+    const size_t cap = need + need / 2 + 4096;
+    CK(cudaMalloc((void**)&c->ws, cap));
+    c->ws_bytes = cap;
+    }
+  CK(cudaMemsetAsync(c->ws, 0, need, c->stream));
+  *ticket = reinterpret_cast<uint32_t*>(c->ws);
+  *desc = reinterpret_cast<uint64_t*>(c->ws + 16);
+  return 1;
+  }
+
+static int big_prepare(tb200_ctx* c, size_t need, uint8_t** out)
+  {
+  if (need > c->big_bytes)
+    {
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->big) CK(cudaFree(c->big));
+    c->big = nullptr; c->big_bytes = 0;
+    CK(cudaMalloc((void**)&c->big, need + 4096));
+    c->big_bytes = need + 4096;
+    }
+  *out = c->big;
+  return 1;
+  }
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes, const tb200_ctx* c)
+  {
+  if (bytes > (size_t)c->max_smem_optin) return fail_msg("kernel needs more shared memory than the device offers");
+  if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 1;
+  }
+
+// ------------------------------------------------------------------------------------------------
+// stream layouts: trico/trico.h:11-34, writers trico/trico.c:215-858
+// ------------------------------------------------------------------------------------------------
+extern "C" int tb200_stream_layout(int type, int* wordsize, int* ncomp, int* per_count)
+  {
+  // codec, wordsize, ncomp, per_count
+  static const int8_t T[21][4] = {
+    {0,0,0,0},
+    {1,4,3,1},{1,8,3,1},{2,4,1,3},{2,8,1,3},{1,4,2,1},{1,8,2,1},{1,4,2,1},{1,8,2,1},
+    {1,4,3,1},{1,8,3,1},{1,4,3,1},{1,8,3,1},{2,4,1,1},{2,4,1,1},{1,4,1,1},{1,8,1,1},
+    {2,1,1,1},{2,2,1,1},{2,4,1,1},{2,8,1,1}};
+  if (type < 1 || type > 20) return 0;
+  if (wordsize) *wordsize = T[type][1];
+  if (ncomp) *ncomp = T[type][2];
+  if (per_count) *per_count = T[type][3];
+  return T[type][0];
+  }
+
+extern "C" int tb200_default_log2_chunk(int type, uint32_t count)
+  {
+  int w = 0, nc = 0, pc = 0;
+  const int codec = tb200_stream_layout(type, &w, &nc, &pc);
+  (void)count;
+  if (codec == 1) return w == 4 ? 9 : 8;     // 512 floats / 256 doubles per chunk (ratio cost <= 1 %)
+  if (codec == 2) return 14;                 // 16 KiB plane blocks
+  return 0;
+  }
+
+extern "C" uint64_t tb200_v1_nchunks(int type, uint32_t count, int log2_chunk)
+  {
+  int w = 0, nc = 0, pc = 0;
+  const int codec = tb200_stream_layout(type, &w, &nc, &pc);
+  if (!codec) return 0;
+  const uint64_t n = (uint64_t)count * pc;
+  const uint64_t nr = (n + ((uint64_t)1 << log2_chunk) - 1) >> log2_chunk;
+  return nr * (codec == 1 ? nc : w);
+  }
+
+extern "C" uint64_t tb200_v1_stream_bound(int type, uint32_t count, int log2_chunk)
+  {
+  int w = 0, nc = 0, pc = 0;
+  const int codec = tb200_stream_layout(type, &w, &nc, &pc);
+  if (!codec) return 0;
+  const uint64_t nch = tb200_v1_nchunks(type, count, log2_chunk);
+  const uint32_t S = 1u << log2_chunk;
+  const uint64_t per = codec == 1 ? fpc_chunk_bound(S, w) : lz4_block_bound(S);
+  return TB200_V1_FIXED_BYTES + nch * (2 + per) + 64;
+  }
+
+// ------------------------------------------------------------------------------------------------
+// chunked FPC
+// ------------------------------------------------------------------------------------------------
+template <typename W, int NCOMP>
+static int launch_fpc_encode(tb200_ctx* c, const FpcEncodeArgs& a)
+  {
+  const uint32_t S = 1u << a.log2S;
+  const uint32_t slot = (fpc_chunk_bound(S, sizeof(W)) + 15u + 16u) & ~15u;
+  const size_t smem = (size_t)FPC_ENC_WARPS * S * sizeof(W) + (size_t)FPC_ENC_WARPS * slot +
+                      (size_t)FPC_ENC_WARPS * ((1u << a.e1) + (1u << a.e2)) * sizeof(W);
+  if (!set_smem(fpc_encode_kernel<W, NCOMP>, smem, c)) return 0;
+  fpc_encode_kernel<W, NCOMP><<<a.ntiles, FPC_ENC_WARPS * 32, smem, c->stream>>>(a);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 1;
+  }
+
+extern "C" int tb200_fpc_encode(tb200_ctx* c, int wordsize, int ncomp, const void* d_in, uint64_t n, int log2_chunk,
+                                int e1, int e2, uint8_t* d_sizes, uint8_t* d_payload, uint8_t* d_total_field, uint64_t* d_total)
+  {
+  CK(cudaSetDevice(c->device));
+  if ((wordsize != 4 && wordsize != 8) || ncomp < 1 || ncomp > 3) return fail_msg("tb200_fpc_encode: bad wordsize/ncomp");
+  if (e1 < 2 || e2 < 2 || e1 > 8 || e2 > 8 || (e1 & 1) || (e2 & 1)) return fail_msg("tb200_fpc_encode: chunk exponents must be even, 2..8");
+  if (log2_chunk < 5 || fpc_chunk_bound(1u << log2_chunk, wordsize) > 65535u) return fail_msg("tb200_fpc_encode: bad chunk size");
+  FpcEncodeArgs a;
+  a.in = d_in; a.n = n; a.log2S = log2_chunk; a.e1 = e1; a.e2 = e2;
+  a.nranges = (uint32_t)((n + ((uint64_t)1 << log2_chunk) - 1) >> log2_chunk);
+  const uint32_t KT = FPC_ENC_WARPS / ncomp;
+  a.ntiles = (a.nranges + KT - 1) / KT;
+  a.sizes = d_sizes; a.payload = d_payload; a.total = d_total;
+  if (a.ntiles == 0)
+    {
+    CK(cudaMemsetAsync(d_total, 0, 8, c->stream));
+    if (d_total_field) CK(cudaMemsetAsync(d_total_field, 0, 8, c->stream));
+    return 1;
+    }
+  if (!ws_prepare(c, a.ntiles + 1, &a.ticket, &a.desc)) return 0;
+  // when the caller does not want the unaligned header copy, point it at scratch
+  a.total_field = d_total_field ? d_total_field : reinterpret_cast<uint8_t*>(a.desc + a.ntiles);
+  if (wordsize == 4)
+    return ncomp == 3 ? launch_fpc_encode<uint32_t, 3>(c, a) : ncomp == 2 ? launch_fpc_encode<uint32_t, 2>(c, a) : launch_fpc_encode<uint32_t, 1>(c, a);
+  return ncomp == 3 ? launch_fpc_encode<uint64_t, 3>(c, a) : ncomp == 2 ? launch_fpc_encode<uint64_t, 2>(c, a) : launch_fpc_encode<uint64_t, 1>(c, a);
+  }
+
+template <typename W, int NCOMP, int R, int SB>
+static int launch_fpc_decode(tb200_ctx* c, FpcDecodeArgs a)
+  {
+  using WIN = FpcWindow<W, SB>;
+  constexpr int NWARPS = NCOMP * R;
+  a.ntiles = (a.nranges + 32 * R - 1) / (32 * R);
+  if (!ws_prepare(c, a.ntiles, &a.ticket, &a.desc)) return 0;
+  const size_t smem = (((size_t)NWARPS * 32 * WIN::WORDS * 4 + 15) & ~(size_t)15) +
+                      (size_t)32 * R * (SB * NCOMP + 1) * sizeof(W) +
+                      (size_t)NWARPS * 32 * ((1u << a.e1) + (1u << a.e2)) * sizeof(W);
+  if (!set_smem(fpc_decode_kernel<W, NCOMP, R, SB>, smem, c)) return 0;
+  fpc_decode_kernel<W, NCOMP, R, SB><<<a.ntiles, NWARPS * 32, smem, c->stream>>>(a);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 1;
+  }
+
+extern "C" int tb200_fpc_decode(tb200_ctx* c, int wordsize, int ncomp, const uint8_t* d_sizes, const uint8_t* d_payload,
+                                uint64_t payload_bytes, uint64_t n, int log2_chunk, int e1, int e2, void* d_out)
+  {
+  CK(cudaSetDevice(c->device));
+  if ((wordsize != 4 && wordsize != 8) || ncomp < 1 || ncomp > 3) return fail_msg("tb200_fpc_decode: bad wordsize/ncomp");
+  if (e1 < 2 || e2 < 2 || e1 > 8 || e2 > 8 || (e1 & 1) || (e2 & 1)) return fail_msg("tb200_fpc_decode: chunk exponents must be even, 2..8");
+  if (log2_chunk < 5 || log2_chunk > 13) return fail_msg("tb200_fpc_decode: bad chunk size");
+  if (n == 0) return 1;
+  FpcDecodeArgs a;
+  a.sizes = d_sizes; a.payload = d_payload; a.payload_bytes = payload_bytes; a.n = n;
+  a.nranges = (uint32_t)((n + ((uint64_t)1 << log2_chunk) - 1) >> log2_chunk);
+  a.ntiles = 0; a.log2S = log2_chunk; a.e1 = e1; a.e2 = e2; a.out = d_out; a.desc = nullptr; a.ticket = nullptr;
+  if (wordsize == 4)
+    return ncomp == 3 ? launch_fpc_decode<uint32_t, 3, 1, 32>(c, a) : ncomp == 2 ? launch_fpc_decode<uint32_t, 2, 2, 32>(c, a) : launch_fpc_decode<uint32_t, 1, 4, 32>(c, a);
+  return ncomp == 3 ? launch_fpc_decode<uint64_t, 3, 1, 16>(c, a) : ncomp == 2 ? launch_fpc_decode<uint64_t, 2, 2, 16>(c, a) : launch_fpc_decode<uint64_t, 1, 4, 16>(c, a);
+  }
+
+// ------------------------------------------------------------------------------------------------
+// reference-format (v0) FPC streams
+// ------------------------------------------------------------------------------------------------
+extern "C" uint64_t tb200_fpc_v0_bound(int wordsize, uint32_t n)
+  {
+  return 5 + (uint64_t)fpc_chunk_bound(0, wordsize) + (wordsize == 4 ? (uint64_t)n * 4 + 3 * (((uint64_t)n + 7) / 8) : (uint64_t)n * 8 + ((uint64_t)n + 1) / 2) + 16;
+  }
+
+static void norm_exponents(int* e1, int* e2)
+  { // floating_point_stream_compression.c:88-93
+  *e1 &= ~1; *e2 &= ~1;
+  if (*e1 > 30) *e1 = 30;
+  if (*e2 > 30) *e2 = 30;
+  }
+
+extern "C" int tb200_fpc_encode_v0(tb200_ctx* c, int wordsize, const void* d_in, uint32_t n, uint32_t stride, int nstreams,
+                                   int e1, int e2, uint8_t* d_out, uint64_t out_stride, uint32_t* d_nbytes)
+  {
+  CK(cudaSetDevice(c->device));
+  if (wordsize != 4 && wordsize != 8) return fail_msg("tb200_fpc_encode_v0: bad wordsize");
+  norm_exponents(&e1, &e2);
+  if (e1 < 2 || e2 < 2) return fail_msg("tb200_fpc_encode_v0: exponents below 2 are not supported");
+  FpcLegacyEncodeArgs a;
+  a.in = d_in; a.n = n; a.stride = stride; a.nstreams = nstreams; a.e1 = e1; a.e2 = e2;
+  a.out = d_out; a.out_stride = out_stride; a.nbytes = d_nbytes; a.gtables = nullptr;
+  const size_t tw = ((size_t)1 << e1) + ((size_t)1 << e2);
+  size_t smem = tw * wordsize;
+  if (smem > 64 * 1024)
+    {
+    uint8_t* g = nullptr;
+    if (!big_prepare(c, tw * wordsize * nstreams, &g)) return 0;
+    a.gtables = g;      // zeroed by the kernel's warp before use
+    smem = 0;
+    }
+  if (wordsize == 4)
+    {
+    if (!set_smem(fpc_encode_legacy_kernel<uint32_t>, smem, c)) return 0;
+    fpc_encode_legacy_kernel<uint32_t><<<nstreams, 32, smem, c->stream>>>(a);
+    }
+  else
+    {
+    if (!set_smem(fpc_encode_legacy_kernel<uint64_t>, smem, c)) return 0;
+    fpc_encode_legacy_kernel<uint64_t><<<nstreams, 32, smem, c->stream>>>(a);
+    }
+  c->launches++;
+  CK(cudaGetLastError());
+  return 1;
+  }
+
+extern "C" int tb200_fpc_decode_v0(tb200_ctx* c, int wordsize, const uint8_t* d_base, const uint64_t* offsets,
+                                   const uint8_t* hash_info, int nstreams, uint32_t expect_n, void* d_out, uint32_t stride)
+  {
+  CK(cudaSetDevice(c->device));
+  if (wordsize != 4 && wordsize != 8) return fail_msg("tb200_fpc_decode_v0: bad wordsize");
+  if (nstreams < 1 || nstreams > 8) return fail_msg("tb200_fpc_decode_v0: bad stream count");
+  size_t tw = 0;
+  for (int s = 0; s < nstreams; ++s)
+    {
+    const size_t t = ((size_t)1 << ((hash_info[s] >> 4) << 1)) + ((size_t)1 << ((hash_info[s] & 15) << 1));
+    if (t > tw) tw = t;
+    }
+  // pointer table + counts live at the start of the big scratch; tables (if global) follow
+  const size_t head = 256;
+  const bool global_tables = tw * wordsize > 64 * 1024;
+  uint8_t* g = nullptr;
+  if (!big_prepare(c, head + (global_tables ? tw * wordsize * nstreams : 0), &g)) return 0;
+  const uint8_t* ptrs[8];
+  for (int s = 0; s < nstreams; ++s) ptrs[s] = d_base + offsets[s];
+  CK(cudaMemcpyAsync(g, ptrs, sizeof(void*) * nstreams, cudaMemcpyHostToDevice, c->stream));
+  FpcLegacyDecodeArgs a;
+  a.streams = reinterpret_cast<const uint8_t* const*>(g);
+  a.nstreams = nstreams; a.out = d_out; a.stride = stride;
+  a.counts = reinterpret_cast<uint32_t*>(g + 128);
+  a.expect = expect_n;
+  a.gtables = nullptr; a.gtable_words = tw;
+  size_t smem = tw * wordsize;
+  if (global_tables)
+    {
+    a.gtables = g + head;
+    CK(cudaMemsetAsync(g + head, 0, tw * wordsize * nstreams, c->stream));
+    smem = 0;
+    }
+  if (wordsize == 4)
+    {
+    if (!set_smem(fpc_decode_legacy_kernel<uint32_t>, smem, c)) return 0;
+    fpc_decode_legacy_kernel<uint32_t><<<nstreams, 32, smem, c->stream>>>(a);
+    }
+  else
+    {
+    if (!set_smem(fpc_decode_legacy_kernel<uint64_t>, smem, c)) return 0;
+    fpc_decode_legacy_kernel<uint64_t><<<nstreams, 32, smem, c->stream>>>(a);
+    }
+  c->launches++;
+  CK(cudaGetLastError());
+  // ptrs[] is a stack array consumed by an async copy from pageable memory: CUDA stages pageable
+  // sources before returning, so no synchronisation is needed here.
+  return 1;
+  }
+
+#include "device_api_lz4.inc"
+#include "device_api_misc.inc"

@@ -1,0 +1,620 @@
+// fpc.cuh - FPC-style (FCM + DFCM predictor, XOR residual, leading-zero-byte code) float/double
+// stream codec for sm_100a.
+//
+// Replaces trico_compress / trico_decompress (+ _double_precision) of the reference:
+//   /root/reference/trico/floating_point_stream_compression.c:86-417 (float), :576-1164 (double).
+//
+// ENCODE is data-parallel inside a chunk.  Both predictors of the reference are finite-context:
+//   FCM  context of value j  = top e1 bits of v[j-1]                       (fpc.c:76-79, :135)
+//   DFCM context of value j  = ((t[j-2] & (2^(e2/2)-1)) << e2/2) ^ t[j-1], t = stride >> (bits-e2)
+//                                                                          (fpc.c:81-84, :142)
+// and the prediction is "what followed the most recent earlier element with the same context"
+// (table store at the old hash, then lookup at the new one, fpc.c:134-136, :141-143).  A warp holds
+// 32 CONSECUTIVE values, finds that earlier element with match.any + shfl inside the window and
+// with a small table (per warp, shared memory) across windows, so the emitted bytes are identical
+// to the serial reference while every instruction works on 32 values.
+//
+// DECODE is inherently serial inside a chunk (the context of value j needs the decoded v[j-1]), so
+// the parallelism is across chunks: one lane per chunk, lane-private tables interleaved in shared
+// memory (bank = lane), compressed bytes staged per warp by coalesced loads, output transposed
+// through shared memory so global stores are contiguous.
+#pragma once
+
+#include "common.cuh"
+
+namespace tb200 {
+
+template <typename W> struct FpcTraits;
+template <> struct FpcTraits<uint32_t>
+  {
+  static constexpr int BITS = 32;     // value width
+  static constexpr int GROUP = 8;     // values per code word            (fpc.c:12-18)
+  static constexpr int CBITS = 3;     // bits per code
+  static constexpr int HDR = 3;       // code word bytes, big-endian
+  static constexpr int BASE2 = 4;     // codes > BASE2 select the DFCM residual (fpc.c:310)
+  static constexpr int WBYTES = 4;
+  };
+template <> struct FpcTraits<uint64_t>
+  {
+  static constexpr int BITS = 64;
+  static constexpr int GROUP = 2;     // fpc.c:421-425
+  static constexpr int CBITS = 4;
+  static constexpr int HDR = 1;
+  static constexpr int BASE2 = 8;     // fpc.c:979
+  static constexpr int WBYTES = 8;
+  };
+
+// worst-case bytes of one chunk payload (groups only, no 5-byte stream header)
+__host__ __device__ constexpr uint32_t fpc_chunk_bound(uint32_t values, int wbytes)
+  {
+  return wbytes == 4 ? values * 4u + 3u * ((values + 7u) / 8u) + 8u
+                     : values * 8u + ((values + 1u) / 2u) + 2u;
+  }
+
+__device__ __forceinline__ int sig_bytes(uint32_t x) { return (39 - __clz((int)x)) >> 3; }
+__device__ __forceinline__ int sig_bytes(uint64_t x) { return (71 - __clzll((long long)x)) >> 3; }
+
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative encoder of one chunk (or, with cnt = whole stream, of a reference v0 stream).
+//   src      values of this component: element j lives at src[j * stride]
+//   out      destination for the groups (code words + residual bytes); any address space
+//   T1, T2   per-warp predictor tables with (1<<e1) / (1<<e2) entries, zeroed here
+// Returns the number of bytes written.  All 32 lanes must call it.
+// ---------------------------------------------------------------------------------------------
+template <typename W, typename SrcPtr>
+__device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride, uint32_t cnt,
+                                                    uint8_t* out, W* T1, W* T2, int e1, int e2)
+  {
+  using TR = FpcTraits<W>;
+  const unsigned lane = lane_id();
+  const unsigned lt = lanemask_lt(), gt = lanemask_gt();
+  for (uint32_t i = lane; i < (1u << e1); i += 32) T1[i] = 0;
+  for (uint32_t i = lane; i < (1u << e2); i += 32) T2[i] = 0;
+  __syncwarp();
+
+  const int h = e2 >> 1;
+  const uint32_t lowmask = (1u << h) - 1u;
+  const uint32_t padlimit = (cnt + TR::GROUP - 1) / TR::GROUP * TR::GROUP;
+  W carry_v = 0;
+  uint32_t carry_ta = 0, carry_tb = 0;      // t[j-1], t[j-2] entering the window
+  uint32_t obase = 0;
+
+  for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
+    {
+    const uint32_t j = i0 + lane;
+    const bool act = j < cnt;
+    const W v = act ? (W)src[(size_t)j * stride] : (W)0;
+    W vprev = __shfl_up_sync(FULL, v, 1);
+    if (lane == 0) vprev = carry_v;
+
+    // FCM: context = top e1 bits of the previous value (initial hash 0 == context of a zero value)
+    const uint32_t c1 = (uint32_t)(vprev >> (TR::BITS - e1));
+    const unsigned m1 = __match_any_sync(FULL, c1);
+    const unsigned early1 = m1 & lt;
+    const int src1 = early1 ? 31 - __clz((int)early1) : (int)lane;
+    const W p1s = __shfl_sync(FULL, v, src1);
+    const W p1t = T1[c1];
+    const W x1 = v ^ (early1 ? p1s : p1t);
+
+    // DFCM: context from the two previous strides
+    const W s = v - vprev;
+    const uint32_t t = (uint32_t)(s >> (TR::BITS - e2));
+    uint32_t ta = __shfl_up_sync(FULL, t, 1);
+    uint32_t tb = __shfl_up_sync(FULL, t, 2);
+    if (lane == 0) { ta = carry_ta; tb = carry_tb; }
+    if (lane == 1) { tb = carry_ta; }
+    const uint32_t c2 = ((tb & lowmask) << h) ^ ta;
+    const unsigned m2 = __match_any_sync(FULL, c2);
+    const unsigned early2 = m2 & lt;
+    const int src2 = early2 ? 31 - __clz((int)early2) : (int)lane;
+    const W p2s = __shfl_sync(FULL, s, src2);
+    const W p2t = T2[c2];
+    const W x2 = v ^ (vprev + (early2 ? p2s : p2t));
+
+    // code selection, fpc.c:146-189 / :635-782
+    const int n1 = sig_bytes(x1);
+    int n2 = sig_bytes(x2); if (n2 == 0) n2 = 1;
+    const bool use2 = (n1 >= 2) && (n2 < n1);
+    int code = use2 ? TR::BASE2 + n2 : n1;
+    int nb = use2 ? n2 : n1;
+    W x = use2 ? x2 : x1;
+    if (!act)
+      { // pad slots of the last group: code 1 + one zero byte (fpc.c:196-204, :789-794)
+      const bool pad = j < padlimit;
+      code = pad ? 1 : 0; nb = pad ? 1 : 0; x = 0;
+      }
+
+    // table update: the last active element of every context wins (what a serial pass leaves)
+    const unsigned actmask = __ballot_sync(FULL, act);
+    if (act && ((m1 & gt & actmask) == 0)) T1[c1] = v;
+    if (act && ((m2 & gt & actmask) == 0)) T2[c2] = s;
+
+    // code word of this lane's group
+    uint32_t bc = (uint32_t)code << (TR::CBITS * (lane & (TR::GROUP - 1)));
+#pragma unroll
+    for (int o = 1; o < TR::GROUP; o <<= 1) bc |= __shfl_xor_sync(FULL, bc, o);
+    const bool leader = ((lane & (TR::GROUP - 1)) == 0) && (j < padlimit);
+
+    // byte offsets: exclusive scan of (header bytes of a group leader + residual bytes)
+    const uint32_t contrib = (uint32_t)nb + (leader ? TR::HDR : 0);
+    uint32_t incl = contrib;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+      {
+      const uint32_t up = __shfl_up_sync(FULL, incl, o);
+      if (lane >= (unsigned)o) incl += up;
+      }
+    uint8_t* p = out + obase + (incl - contrib);
+    if (leader)
+      {
+      if (TR::HDR == 3) { p[0] = (uint8_t)(bc >> 16); p[1] = (uint8_t)(bc >> 8); p[2] = (uint8_t)bc; }
+      else              { p[0] = (uint8_t)bc; }
+      p += TR::HDR;
+      }
+#pragma unroll
+    for (int b = 0; b < TR::WBYTES; ++b)
+      if (b < nb) p[b] = (uint8_t)(x >> (8 * (nb - 1 - b)));
+
+    obase += __shfl_sync(FULL, incl, 31);
+    carry_v = __shfl_sync(FULL, v, 31);
+    carry_tb = __shfl_sync(FULL, t, 30);
+    carry_ta = __shfl_sync(FULL, t, 31);
+    __syncwarp();
+    }
+  return obase;
+  }
+
+// ---------------------------------------------------------------------------------------------
+// K3: chunked encode, fused with the AoS -> SoA transpose and the archive assembly.
+// Tile = KT = 12/NCOMP consecutive chunk ranges x NCOMP components = 12 chunks, one warp each.
+//   1. the CTA stages the tile's AoS elements in shared memory with 16-byte coalesced loads
+//      (this is the reference's trico_transpose_*_aos_to_soa, transpose_aos_to_soa.c:8-82, fused)
+//   2. every warp encodes its chunk into a shared-memory slot
+//   3. chunk sizes -> block prefix -> decoupled look-back over tiles -> payload written once, at
+//      its final offset; the u16 size table and the stream header are written by the same kernel.
+// ---------------------------------------------------------------------------------------------
+struct FpcEncodeArgs
+  {
+  const void* in;          // device, AoS: n * ncomp words
+  uint64_t n;              // values per component
+  uint32_t nranges;        // ceil(n / S)
+  uint32_t ntiles;
+  int log2S, e1, e2;
+  uint8_t* sizes;          // u16 LE [nranges * ncomp] (may be unaligned inside an archive)
+  uint8_t* payload;        // chunk payloads, packed
+  uint8_t* total_field;    // 8 bytes (unaligned): payload byte count, little-endian (stream header)
+  uint64_t* total;         // aligned device scalar with the same value
+  uint64_t* desc;          // look-back descriptors [ntiles], zeroed
+  uint32_t* ticket;        // zeroed
+  };
+
+constexpr int FPC_ENC_WARPS = 12;
+
+template <typename W, int NCOMP>
+__global__ void __launch_bounds__(FPC_ENC_WARPS * 32)
+fpc_encode_kernel(const FpcEncodeArgs a)
+  {
+  constexpr int KT = FPC_ENC_WARPS / NCOMP;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t S = 1u << a.log2S;
+  const uint32_t slot = (fpc_chunk_bound(S, sizeof(W)) + 15u + 16u) & ~15u;
+  W* tile_in = reinterpret_cast<W*>(smem_raw);                                   // KT*S*NCOMP words
+  uint8_t* stage = smem_raw + (size_t)FPC_ENC_WARPS * S * sizeof(W);             // 12 slots
+  W* tables = reinterpret_cast<W*>(stage + (size_t)FPC_ENC_WARPS * slot);        // per warp T1|T2
+  __shared__ uint32_t sh_tile;
+  __shared__ uint32_t sh_size[FPC_ENC_WARPS];
+  __shared__ uint32_t sh_off[FPC_ENC_WARPS];
+  __shared__ uint64_t sh_base;
+
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  if (threadIdx.x == 0) sh_tile = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = sh_tile;
+
+  // 1. stage the AoS tile
+  const uint64_t k0 = (uint64_t)tile * KT;
+  const uint64_t v_lo = k0 << a.log2S;
+  uint64_t v_hi = (k0 + KT) << a.log2S; if (v_hi > a.n) v_hi = a.n;
+  const uint32_t nwords = (uint32_t)(v_hi - v_lo) * NCOMP;
+  const W* gin = reinterpret_cast<const W*>(a.in) + v_lo * NCOMP;
+  if ((reinterpret_cast<uintptr_t>(gin) & 15u) == 0)
+    {
+    constexpr int PER = 16 / sizeof(W);
+    const uint32_t nvec = nwords / PER;
+    const uint4* g4 = reinterpret_cast<const uint4*>(gin);
+    uint4* s4 = reinterpret_cast<uint4*>(tile_in);
+    for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) s4[i] = __ldg(g4 + i);
+    for (uint32_t i = nvec * PER + threadIdx.x; i < nwords; i += blockDim.x) tile_in[i] = gin[i];
+    }
+  else
+    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) tile_in[i] = gin[i];
+  __syncthreads();
+
+  // 2. one chunk per warp
+  const uint32_t kk = warp / NCOMP, c = warp % NCOMP;
+  const uint64_t k = k0 + kk;
+  uint32_t nbytes = 0;
+  if (k < a.nranges)
+    {
+    const uint64_t lo = k << a.log2S;
+    const uint32_t cnt = (uint32_t)((a.n - lo < S) ? (a.n - lo) : S);
+    W* T1 = tables + (size_t)warp * ((1u << a.e1) + (1u << a.e2));
+    W* T2 = T1 + (1u << a.e1);
+    nbytes = fpc_encode_warp<W>(tile_in + (size_t)kk * S * NCOMP + c, NCOMP, cnt, stage + (size_t)warp * slot, T1, T2, a.e1, a.e2);
+    }
+  if (lane == 0) sh_size[warp] = nbytes;
+  __syncthreads();
+
+  // 3. offsets and assembly.  Chunk order in the stream is (range, component) = warp order.
+  if (warp == 0)
+    {
+    uint32_t mine = lane < FPC_ENC_WARPS ? sh_size[lane] : 0, incl = mine;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1)
+      {
+      const uint32_t up = __shfl_up_sync(FULL, incl, o);
+      if (lane >= (unsigned)o) incl += up;
+      }
+    if (lane < FPC_ENC_WARPS) sh_off[lane] = incl - mine;
+    const uint64_t agg = __shfl_sync(FULL, incl, FPC_ENC_WARPS - 1);
+    const uint64_t excl = lookback_exclusive(a.desc, tile, agg);
+    if (lane == 0)
+      {
+      sh_base = excl;
+      if (tile == a.ntiles - 1)
+        {
+        *a.total = excl + agg;
+        store_u64_bytes(a.total_field, excl + agg);
+        }
+      }
+    }
+  __syncthreads();
+  if (k < a.nranges)
+    {
+    warp_copy_smem_to_global(a.payload + sh_base + sh_off[warp], stage + (size_t)warp * slot, nbytes);
+    if (lane == 0)
+      {
+      uint8_t* sz = a.sizes + 2 * (k * NCOMP + c);
+      sz[0] = (uint8_t)nbytes; sz[1] = (uint8_t)(nbytes >> 8);
+      }
+    }
+  }
+
+// ---------------------------------------------------------------------------------------------
+// Legacy (reference v0) stream encoder: one warp per component stream, whole stream as one chain,
+// same warp routine with cnt = n.  Tables live in global memory when they do not fit in shared
+// memory ((20,20) doubles: 2 x 8 MiB, fpc.c:588-594).  Output bytes go straight to global memory.
+// ---------------------------------------------------------------------------------------------
+struct FpcLegacyEncodeArgs
+  {
+  const void* in;          // device: component c, element j at in[(j * stride + c)]
+  uint32_t n;
+  uint32_t stride;
+  int nstreams;            // components; stream c is encoded by block c
+  int e1, e2;
+  uint8_t* out;            // nstreams slots of out_stride bytes: 5-byte header + groups
+  uint64_t out_stride;
+  uint32_t* nbytes;        // [nstreams]
+  void* gtables;           // nullptr, or nstreams * ((1<<e1)+(1<<e2)) words of global scratch
+  };
+
+template <typename W>
+__global__ void __launch_bounds__(32)
+fpc_encode_legacy_kernel(const FpcLegacyEncodeArgs a)
+  {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const unsigned c = blockIdx.x, lane = lane_id();
+  const size_t tw = ((size_t)1 << a.e1) + ((size_t)1 << a.e2);
+  W* T1 = a.gtables ? reinterpret_cast<W*>(a.gtables) + (size_t)c * tw : reinterpret_cast<W*>(smem_raw);
+  W* T2 = T1 + ((size_t)1 << a.e1);
+  uint8_t* out = a.out + (size_t)c * a.out_stride;
+  if (lane == 0)
+    {
+    out[0] = (uint8_t)(((a.e1 >> 1) << 4) | (a.e2 >> 1));                 // fpc.c:120
+    out[1] = (uint8_t)(a.n >> 24); out[2] = (uint8_t)(a.n >> 16);          // fpc.c:123-126
+    out[3] = (uint8_t)(a.n >> 8);  out[4] = (uint8_t)a.n;
+    }
+  const W* src = reinterpret_cast<const W*>(a.in) + c;
+  uint32_t nb;
+  if (a.n == 0)
+    { // the reference emits one group of pad slots here (slot 0 from uninitialised stack, fpc.c:196-204)
+    using TR = FpcTraits<W>;
+    if (lane == 0)
+      {
+      uint32_t bc = 0;
+      for (int g = 0; g < TR::GROUP; ++g) bc |= 1u << (TR::CBITS * g);
+      uint8_t* p = out + 5;
+      if (TR::HDR == 3) { p[0] = (uint8_t)(bc >> 16); p[1] = (uint8_t)(bc >> 8); p[2] = (uint8_t)bc; } else p[0] = (uint8_t)bc;
+      for (int g = 0; g < TR::GROUP; ++g) p[TR::HDR + g] = 0;
+      }
+    nb = TR::HDR + TR::GROUP;
+    }
+  else
+    nb = fpc_encode_warp<W>(src, a.stride, a.n, out + 5, T1, T2, a.e1, a.e2);
+  if (lane == 0) a.nbytes[c] = nb + 5;
+  }
+
+// ---------------------------------------------------------------------------------------------
+// Lane-serial decoder core.  `Fetch` returns the next `nb` residual bytes as a big-endian value.
+// ---------------------------------------------------------------------------------------------
+template <typename W> struct FpcLaneState
+  {
+  W pred1, pred2, last;
+  uint32_t c1, c2;
+  };
+
+// One value: select the predictor by code, rebuild v, update both tables exactly like the
+// reference decoder (fpc.c:308-326 / :977-995).  TSTRIDE = distance between table entries
+// (32 for lane-interleaved shared-memory tables, 1 for plain arrays).
+template <typename W, int TSTRIDE>
+__device__ __forceinline__ W fpc_decode_value(FpcLaneState<W>& st, W x, bool use2, W* T1, W* T2, int e1, int e2, uint32_t m2)
+  {
+  using TR = FpcTraits<W>;
+  const W v = x ^ (use2 ? st.pred2 : st.pred1);
+  T1[(size_t)st.c1 * TSTRIDE] = v;
+  st.c1 = (uint32_t)(v >> (TR::BITS - e1));
+  st.pred1 = T1[(size_t)st.c1 * TSTRIDE];
+  const W s = v - st.last;
+  T2[(size_t)st.c2 * TSTRIDE] = s;
+  st.c2 = ((st.c2 << (e2 >> 1)) ^ (uint32_t)(s >> (TR::BITS - e2))) & m2;
+  st.pred2 = v + T2[(size_t)st.c2 * TSTRIDE];
+  st.last = v;
+  return v;
+  }
+
+// ---------------------------------------------------------------------------------------------
+// K4: chunked decode fused with the SoA -> AoS transpose.
+// CTA = NCOMP * R warps.  Warp w owns component c = w % NCOMP of 32 consecutive chunk ranges
+// (lane = range), so a CTA owns 32*R ranges x NCOMP components and its output region is one
+// contiguous slab of the AoS array.  Per sub-block of SB values:
+//   a. the warp refreshes every lane's byte window from global memory with coalesced loads
+//   b. every lane decodes SB values of its own chunk out of its window
+//   c. values go to a [range][SB*NCOMP (+1 pad)] shared tile, then out as contiguous rows.
+// ---------------------------------------------------------------------------------------------
+struct FpcDecodeArgs
+  {
+  const uint8_t* sizes;    // u16 LE [nranges * ncomp]
+  const uint8_t* payload;
+  uint64_t payload_bytes;
+  uint64_t n;
+  uint32_t nranges;
+  uint32_t ntiles;
+  int log2S, e1, e2;
+  void* out;               // device AoS
+  uint64_t* desc;          // look-back descriptors, zeroed
+  uint32_t* ticket;        // zeroed
+  };
+
+template <typename W, int SB> struct FpcWindow
+  {
+  using TR = FpcTraits<W>;
+  // bytes one sub-block can consume + 3 bytes of misalignment, in 32-bit words, made odd
+  static constexpr int BYTES = (SB / TR::GROUP) * TR::HDR + SB * TR::WBYTES + 3;
+  static constexpr int WORDS0 = (BYTES + 3) / 4 + 1;      // +1: the unaligned fetch reads one word further
+  static constexpr int WORDS = WORDS0 | 1;
+  };
+
+template <typename W, int NCOMP, int R, int SB>
+__global__ void __launch_bounds__(NCOMP * R * 32)
+fpc_decode_kernel(const FpcDecodeArgs a)
+  {
+  using TR = FpcTraits<W>;
+  using WIN = FpcWindow<W, SB>;
+  constexpr int NWARPS = NCOMP * R;
+  constexpr int NTHREADS = NWARPS * 32;
+  constexpr int ROW = SB * NCOMP + 1;                     // staging row stride (odd: conflict-free column writes)
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t nt1 = 1u << a.e1, nt2 = 1u << a.e2;
+  uint32_t* win = reinterpret_cast<uint32_t*>(smem_raw);                               // [NWARPS][32][WIN::WORDS]
+  W* stagebuf = reinterpret_cast<W*>(smem_raw + ((size_t)NWARPS * 32 * WIN::WORDS * 4 + 15 & ~(size_t)15)); // [32*R][ROW]
+  W* tables = stagebuf + (size_t)32 * R * ROW;                                         // [NWARPS][nt1+nt2][32]
+  __shared__ uint32_t sh_tile;
+  __shared__ uint32_t sh_scan[NTHREADS];
+  __shared__ uint32_t sh_wsum[NWARPS];
+  __shared__ uint64_t sh_base;
+
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  if (threadIdx.x == 0) sh_tile = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = sh_tile;
+
+  // chunk offsets: block-exclusive scan of the tile's sizes in stream order, tile base by look-back
+  const uint64_t nchunks = (uint64_t)a.nranges * NCOMP;
+  const uint64_t g0 = (uint64_t)tile * NTHREADS;
+  uint32_t mysz = 0;
+  if (g0 + threadIdx.x < nchunks)
+    {
+    const uint8_t* sz = a.sizes + 2 * (g0 + threadIdx.x);
+    mysz = (uint32_t)sz[0] | ((uint32_t)sz[1] << 8);
+    }
+  uint32_t incl = mysz;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    {
+    const uint32_t up = __shfl_up_sync(FULL, incl, o);
+    if (lane >= (unsigned)o) incl += up;
+    }
+  if (lane == 31) sh_wsum[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0, tsum = 0;
+#pragma unroll
+  for (int w = 0; w < NWARPS; ++w) { const uint32_t t = sh_wsum[w]; if (w < (int)warp) wbase += t; tsum += t; }
+  sh_scan[threadIdx.x] = wbase + incl - mysz;
+  if (warp == 0)
+    {
+    const uint64_t excl = lookback_exclusive(a.desc, tile, tsum);
+    if (lane == 0) sh_base = excl;
+    }
+  __syncthreads();
+
+  // this lane's chunk
+  const uint32_t c = warp % NCOMP, rgrp = warp / NCOMP;
+  const uint32_t klocal = rgrp * 32 + lane;
+  const uint64_t k = (uint64_t)tile * (32 * R) + klocal;
+  const uint32_t S = 1u << a.log2S;
+  uint32_t cnt = 0;
+  uint64_t pos = 0;                                        // byte offset of the next unread byte in payload
+  if (k < a.nranges)
+    {
+    const uint64_t lo = k << a.log2S;
+    cnt = (uint32_t)((a.n - lo < S) ? (a.n - lo) : S);
+    pos = sh_base + sh_scan[klocal * NCOMP + c];
+    }
+  // number of sub-blocks = that of the fullest chunk in the CTA (range 0 of the tile is never shorter)
+  const uint64_t lo0 = ((uint64_t)tile * (32 * R)) << a.log2S;
+  const uint32_t cnt0 = (uint32_t)((a.n - lo0 < S) ? (a.n - lo0) : S);
+
+  W* T1 = tables + (size_t)warp * (nt1 + nt2) * 32 + lane;
+  W* T2 = T1 + (size_t)nt1 * 32;
+  for (uint32_t i = 0; i < nt1 + nt2; ++i) T1[(size_t)i * 32] = 0;
+  FpcLaneState<W> st; st.pred1 = 0; st.pred2 = 0; st.last = 0; st.c1 = 0; st.c2 = 0;
+  const uint32_t m2 = nt2 - 1;
+
+  uint32_t* wrow = win + ((size_t)warp * 32 + lane) * WIN::WORDS;
+  uint32_t* wwarp = win + (size_t)warp * 32 * WIN::WORDS;
+  const uint8_t* pay_last = a.payload + ((a.payload_bytes ? a.payload_bytes - 1 : 0) & ~(uint64_t)3);   // last readable word start (payload is 4-aligned or clamped below)
+  W* srow = stagebuf + (size_t)klocal * ROW + c;
+  W* gout = reinterpret_cast<W*>(a.out);
+
+  for (uint32_t i0 = 0; i0 < cnt0; i0 += SB)
+    {
+    // a. refresh the windows of all 32 lanes of this warp (coalesced 4-byte loads)
+#pragma unroll 4
+    for (int l = 0; l < 32; ++l)
+      {
+      const uint64_t p = __shfl_sync(FULL, pos, l);
+      const uint8_t* base = a.payload + (p & ~(uint64_t)3) - ((uintptr_t)a.payload & 3);   // word-aligned address at or below the byte
+      for (int w = lane; w < WIN::WORDS; w += 32)
+        {
+        const uint8_t* q = base + 4 * w;
+        if (q > pay_last) q = pay_last - ((uintptr_t)pay_last & 3);
+        wwarp[l * WIN::WORDS + w] = *reinterpret_cast<const uint32_t*>(q);
+        }
+      }
+    __syncwarp();
+
+    // b. decode up to SB values of this lane's chunk
+    uint32_t bp = (uint32_t)(((uintptr_t)a.payload + pos) & 3);
+    const uint32_t bp0 = bp;
+    const uint32_t todo = (i0 < cnt) ? ((cnt - i0 < (uint32_t)SB) ? cnt - i0 : (uint32_t)SB) : 0;
+#pragma unroll 1
+    for (uint32_t g = 0; g < (uint32_t)SB / TR::GROUP; ++g)
+      {
+      if (g * TR::GROUP >= todo) break;
+      // code word
+      uint32_t bc;
+        {
+        const uint32_t wi = bp >> 2;
+        const uint32_t be = __byte_perm(wrow[wi], wrow[wi + 1], 0x0123u + (bp & 3u) * 0x1111u);
+        bc = be >> (32 - 8 * TR::HDR);
+        bp += TR::HDR;
+        }
+#pragma unroll
+      for (int jj = 0; jj < TR::GROUP; ++jj)
+        {
+        const uint32_t code = (bc >> (TR::CBITS * jj)) & ((1u << TR::CBITS) - 1u);
+        const bool use2 = code > (uint32_t)TR::BASE2;
+        const uint32_t nb = use2 ? code - TR::BASE2 : code;
+        W x;
+        const uint32_t wi = bp >> 2;
+        const uint32_t sel = 0x0123u + (bp & 3u) * 0x1111u;
+        if (sizeof(W) == 4)
+          {
+          const uint32_t be = __byte_perm(wrow[wi], wrow[wi + 1], sel);
+          x = (W)__funnelshift_lc(be, 0u, 8u * nb);
+          }
+        else
+          {
+          const uint32_t w0 = wrow[wi], w1 = wrow[wi + 1], w2 = wrow[wi + 2];
+          const uint64_t be = ((uint64_t)__byte_perm(w0, w1, sel) << 32) | __byte_perm(w1, w2, sel);
+          x = nb ? (W)(be >> (64 - 8 * nb)) : (W)0;
+          }
+        bp += nb;
+        const uint32_t idx = g * TR::GROUP + jj;
+        if (idx < todo)
+          {
+          const W v = fpc_decode_value<W, 32>(st, x, use2, T1, T2, a.e1, a.e2, m2);
+          srow[(size_t)idx * NCOMP] = v;
+          }
+        }
+      }
+    pos += bp - bp0;
+    __syncthreads();
+
+    // c. flush the staged slab: row r = range (tile*32R + r), values [i0, i0+SB) x NCOMP, contiguous
+    for (uint32_t r = warp; r < 32u * R; r += NWARPS)
+      {
+      const uint64_t kr = (uint64_t)tile * (32 * R) + r;
+      if (kr >= a.nranges) break;
+      const uint64_t lo = kr << a.log2S;
+      const uint32_t rc = (uint32_t)((a.n - lo < S) ? (a.n - lo) : S);
+      if (i0 >= rc) continue;
+      const uint32_t nv = ((rc - i0 < (uint32_t)SB) ? rc - i0 : (uint32_t)SB) * NCOMP;
+      const W* sr = stagebuf + (size_t)r * ROW;
+      W* go = gout + (lo + i0) * NCOMP;
+      for (uint32_t q = lane; q < nv; q += 32) go[q] = sr[q];
+      }
+    __syncthreads();
+    }
+  }
+
+// ---------------------------------------------------------------------------------------------
+// K4L: legacy (reference v0) stream decoder.  The whole stream is ONE serial chain
+// (fpc.c:246-327), so a stream is decoded by a single lane; block b decodes stream b.
+// Tables: shared memory when they fit, else global scratch (zeroed by the host).
+// ---------------------------------------------------------------------------------------------
+struct FpcLegacyDecodeArgs
+  {
+  const uint8_t* const* streams;   // device array of nstreams pointers to streams (hash_info, n, groups)
+  int nstreams;
+  void* out;                       // element j of stream c goes to out[j * stride + c]
+  uint32_t stride;
+  void* gtables;                   // nullptr or nstreams * table words of zeroed scratch
+  uint64_t gtable_words;           // per stream
+  uint32_t* counts;                // [nstreams] decoded value counts (from the stream headers)
+  uint32_t expect;                 // values the caller has room for per stream
+  };
+
+template <typename W>
+__global__ void __launch_bounds__(32)
+fpc_decode_legacy_kernel(const FpcLegacyDecodeArgs a)
+  {
+  using TR = FpcTraits<W>;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const unsigned c = blockIdx.x;
+  const uint8_t* p = a.streams[c];
+  const int e1 = (p[0] >> 4) << 1, e2 = (p[0] & 15) << 1;          // fpc.c:214-217
+  const uint32_t n = ((uint32_t)p[1] << 24) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 8) | p[4];
+  const size_t nt1 = (size_t)1 << e1, nt2 = (size_t)1 << e2;
+  W* T1; W* T2;
+  const bool in_smem = a.gtables == nullptr;
+  if (in_smem) { T1 = reinterpret_cast<W*>(smem_raw); for (size_t i = threadIdx.x; i < nt1 + nt2; i += 32) T1[i] = 0; }
+  else T1 = reinterpret_cast<W*>(a.gtables) + (size_t)c * a.gtable_words;
+  T2 = T1 + nt1;
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  a.counts[c] = n;
+  const uint32_t todo = n < a.expect ? n : a.expect;
+  p += 5;
+  FpcLaneState<W> st; st.pred1 = 0; st.pred2 = 0; st.last = 0; st.c1 = 0; st.c2 = 0;
+  const uint32_t m2 = (uint32_t)nt2 - 1;
+  W* out = reinterpret_cast<W*>(a.out) + c;
+  for (uint32_t i = 0; i < todo; i += TR::GROUP)
+    {
+    uint32_t bc = 0;
+    for (int b = 0; b < TR::HDR; ++b) bc = (bc << 8) | *p++;
+#pragma unroll
+    for (int jj = 0; jj < TR::GROUP; ++jj)
+      {
+      const uint32_t code = (bc >> (TR::CBITS * jj)) & ((1u << TR::CBITS) - 1u);
+      const bool use2 = code > (uint32_t)TR::BASE2;
+      const uint32_t nb = use2 ? code - TR::BASE2 : code;
+      W x = 0;
+      for (uint32_t b = 0; b < nb; ++b) x = (x << 8) | *p++;
+      if (i + jj < todo)
+        out[(size_t)(i + jj) * a.stride] = fpc_decode_value<W, 1>(st, x, use2, T1, T2, e1, e2, m2);
+      }
+    }
+  }
+
+} // namespace tb200

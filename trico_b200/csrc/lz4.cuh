@@ -1,0 +1,458 @@
+// lz4.cuh - LZ4 *block format* compressor / decompressor for sm_100a, one warp per block.
+//
+// Replaces the bundled LZ4 v1.9.2 calls of the reference:
+//   LZ4_compress_default  /root/reference/lz4/lz4.c:1271 (LZ4_compress_generic :793-1181)
+//   LZ4_decompress_safe   /root/reference/lz4/lz4.c:2078 (LZ4_decompress_generic :1657-2072)
+// The compressor is a greedy single-pass hash matcher like the reference's, but tests 32
+// consecutive positions per step (one per lane) and inserts every scanned position; its output is
+// a valid LZ4 block (last 5 bytes literal, last match starts >= 12 bytes before the end,
+// lz4.c:189-196) but not byte-identical to the CPU library - the format, not the parse, is the
+// contract.  The decompressor accepts any valid block, including the reference's.
+#pragma once
+
+#include "common.cuh"
+
+namespace tb200 {
+
+constexpr uint32_t LZ4_MINMATCH = 4;
+constexpr uint32_t LZ4_LASTLITERALS = 5;     // lz4.c:192
+constexpr uint32_t LZ4_MFLIMIT = 12;         // lz4.c:193
+
+__host__ __device__ constexpr uint32_t lz4_block_bound(uint32_t n) { return n + n / 255u + 16u; }   // lz4.h:171
+
+// unaligned little-endian 32-bit read from shared memory
+__device__ __forceinline__ uint32_t smem_read32(const uint8_t* base, uint32_t pos)
+  {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (pos >> 2);
+  return __funnelshift_r(w[0], w[1], (pos & 3u) * 8u);
+  }
+
+// Emits one sequence (warp-cooperative).  `mlen` = 0 means "last sequence, literals only".
+// Returns the new output position.
+template <typename DstPtr>
+__device__ __forceinline__ uint32_t lz4_emit(DstPtr dst, uint32_t op, const uint8_t* src, uint32_t lit_start,
+                                             uint32_t nlit, uint32_t offset, uint32_t mlen)
+  {
+  const unsigned lane = lane_id();
+  const uint32_t m = mlen ? mlen - LZ4_MINMATCH : 0;
+  const uint32_t next = nlit >= 15 ? (nlit - 15) / 255 + 1 : 0;       // literal-length extension bytes
+  if (lane == 0) dst[op] = (uint8_t)(((nlit >= 15 ? 15u : nlit) << 4) | (m >= 15 ? 15u : m));
+  for (uint32_t i = lane; i < next; i += 32) dst[op + 1 + i] = (i + 1 == next) ? (uint8_t)((nlit - 15) % 255) : (uint8_t)255;
+  op += 1 + next;
+  for (uint32_t i = lane; i < nlit; i += 32) dst[op + i] = src[lit_start + i];
+  op += nlit;
+  if (mlen)
+    {
+    const uint32_t mext = m >= 15 ? (m - 15) / 255 + 1 : 0;
+    if (lane == 0) { dst[op] = (uint8_t)offset; dst[op + 1] = (uint8_t)(offset >> 8); }
+    for (uint32_t i = lane; i < mext; i += 32) dst[op + 2 + i] = (i + 1 == mext) ? (uint8_t)((m - 15) % 255) : (uint8_t)255;
+    op += 2 + mext;
+    }
+  return op;
+  }
+
+// Compresses src[0..n) (shared memory, readable 8 bytes past n) into dst.  `table` = HSIZE u16
+// entries of shared memory private to the warp.  n <= 65535.  Returns compressed size.
+template <int HLOG, typename DstPtr>
+__device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* table)
+  {
+  const unsigned lane = lane_id();
+  const unsigned gt = lanemask_gt();
+  uint32_t op = 0, anchor = 0;
+  if (n >= LZ4_MFLIMIT + 1)
+    {
+    for (uint32_t i = lane; i < (1u << HLOG); i += 32) table[i] = 0;
+    __syncwarp();
+    const uint32_t mflimit = n - LZ4_MFLIMIT;        // last position where a match may start
+    const uint32_t matchlimit = n - LZ4_LASTLITERALS;
+    uint32_t p = 0;
+    while (p <= mflimit)
+      {
+      const uint32_t q = p + lane;
+      const bool valid = q <= mflimit;
+      const uint32_t seq = valid ? smem_read32(src, q) : 0u;
+      const uint32_t h = (seq * 2654435761u) >> (32 - HLOG);
+      const uint32_t cand = table[h];
+      __syncwarp();
+      // deterministic insertion: among lanes with the same bucket the highest position wins
+      const unsigned same = __match_any_sync(FULL, valid ? h : (0x80000000u | lane));
+      if (valid && (same & gt) == 0) table[h] = (uint16_t)q;
+      const bool ok = valid && cand < q && smem_read32(src, cand) == seq;
+      const unsigned mask = __ballot_sync(FULL, ok);
+      __syncwarp();
+      if (mask == 0) { p += 32; continue; }
+      const int f = __ffs((int)mask) - 1;
+      const uint32_t mq = p + (uint32_t)f;
+      const uint32_t mc = __shfl_sync(FULL, cand, f);
+      // forward extension, 32 bytes per step
+      uint32_t len = LZ4_MINMATCH;
+      for (;;)
+        {
+        const uint32_t idx = mq + len + lane;
+        const bool eq = idx < matchlimit && src[idx] == src[mc + len + lane];
+        const unsigned ne = __ballot_sync(FULL, !eq);
+        if (ne == 0) { len += 32; continue; }
+        len += (uint32_t)__ffs((int)ne) - 1u;
+        break;
+        }
+      op = lz4_emit(dst, op, src, anchor, mq - anchor, mq - mc, len);
+      p = anchor = mq + len;
+      }
+    }
+  op = lz4_emit(dst, op, src, anchor, n - anchor, 0, 0);
+  return op;
+  }
+
+// Warp-cooperative LZ4 block decoder.  src: compressed bytes (global).  dst: output; with
+// DST_GLOBAL the match source is re-read from global memory behind a warp fence (legacy whole-plane
+// blocks), otherwise dst is shared memory.  Returns the number of bytes produced, or 0xffffffff on
+// a malformed block (out-of-range offset / overrun), in which case output is unspecified.
+template <bool DST_GLOBAL>
+__device__ __forceinline__ uint32_t lz4_decompress_warp(const uint8_t* __restrict__ src, uint32_t src_len,
+                                                        uint8_t* dst, uint32_t dst_cap)
+  {
+  const unsigned lane = lane_id();
+  uint32_t ip = 0, op = 0;
+  if (src_len == 0) return 0xffffffffu;
+  for (;;)
+    {
+    if (ip >= src_len) return 0xffffffffu;
+    const uint32_t token = src[ip++];
+    uint32_t lit = token >> 4;
+    if (lit == 15)
+      {
+      uint32_t b;
+      do { if (ip >= src_len) return 0xffffffffu; b = src[ip++]; lit += b; } while (b == 255);
+      }
+    if (ip + lit > src_len || op + lit > dst_cap) return 0xffffffffu;
+    for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = src[ip + i];
+    ip += lit; op += lit;
+    if (ip >= src_len) break;                       // last sequence has no match part
+    if (ip + 2 > src_len) return 0xffffffffu;
+    const uint32_t offset = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
+    ip += 2;
+    uint32_t mlen = token & 15u;
+    if (mlen == 15)
+      {
+      uint32_t b;
+      do { if (ip >= src_len) return 0xffffffffu; b = src[ip++]; mlen += b; } while (b == 255);
+      }
+    mlen += LZ4_MINMATCH;
+    if (offset == 0 || offset > op || op + mlen > dst_cap) return 0xffffffffu;
+    if (DST_GLOBAL) { __threadfence_block(); }
+    __syncwarp();                                   // literals of this sequence are visible
+    // Overlapping copy: byte k of the match equals byte (k mod offset) of the `offset` bytes
+    // before op, all of which are already written.
+    const uint8_t* ms = dst + op - offset;
+    if (offset >= mlen || offset >= 32)
+      {
+      // chunks of at most `offset` bytes never read what they write within a step
+      const uint32_t step = offset >= 32 ? 32u : offset;   // offset >= mlen: one pass of <= 32-byte strides is still safe
+      if (offset >= mlen)
+        for (uint32_t i = lane; i < mlen; i += 32) dst[op + i] = DST_GLOBAL ? __ldcg(ms + i) : ms[i];
+      else
+        for (uint32_t base = 0; base < mlen; base += step)
+          {
+          const uint32_t i = base + lane;
+          if (lane < step && i < mlen) dst[op + i] = DST_GLOBAL ? __ldcg(ms + i) : ms[i];
+          if (DST_GLOBAL) __threadfence_block();
+          __syncwarp();
+          }
+      }
+    else
+      {
+      // short period (offset < 32 and < mlen): replicate the period
+      for (uint32_t i = lane; i < mlen; i += 32) dst[op + i] = DST_GLOBAL ? __ldcg(ms + (i % offset)) : ms[i % offset];
+      }
+    op += mlen;
+    if (DST_GLOBAL) __threadfence_block();
+    __syncwarp();
+    }
+  return op;
+  }
+
+// ---------------------------------------------------------------------------------------------
+// K2 + K5: byte-plane split (trico_transpose_uint{16,32,64}_aos_to_soa,
+// transpose_aos_to_soa.c:84-147) fused with per-plane-block LZ4 compression and the assembly.
+// Persistent CTAs of WB warps (WB = element bytes).  Per tile (= one range of B elements):
+//   1. coalesced 16-byte loads of the AoS elements, byte planes written to shared memory
+//   2. warp p compresses plane p into the CTA's scratch slot (global, reused -> L2 resident)
+//   3. sizes -> look-back over tiles -> warp p copies its block to the final offset.
+// ---------------------------------------------------------------------------------------------
+struct Lz4EncodeArgs
+  {
+  const void* in;          // device, n elements of WB bytes
+  uint64_t n;
+  uint32_t nranges;        // == ntiles
+  int log2B;
+  uint8_t* sizes;          // u16 LE [nranges * WB]
+  uint8_t* payload;
+  uint8_t* total_field;
+  uint64_t* total;
+  uint8_t* scratch;        // gridDim.x * WB * slot bytes
+  uint32_t slot;           // bytes per scratch slot (>= lz4_block_bound(B), multiple of 16)
+  uint64_t* desc;
+  uint32_t* ticket;
+  };
+
+constexpr int LZ4_HLOG = 12;     // 4096 u16 entries = 8 KiB per warp
+
+template <int WB>
+__global__ void __launch_bounds__(WB * 32)
+lz4_encode_kernel(const Lz4EncodeArgs a)
+  {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t B = 1u << a.log2B;
+  const uint32_t pstride = B + 16;                                   // plane buffers padded for read-ahead
+  uint8_t* planes = smem_raw;                                        // [WB][pstride]
+  uint16_t* tables = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WB * pstride);   // [WB][1<<HLOG]
+  __shared__ uint32_t sh_tile;
+  __shared__ uint32_t sh_size[WB];
+  __shared__ uint64_t sh_base;
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  uint8_t* my_scratch = a.scratch + ((size_t)blockIdx.x * WB + warp) * a.slot;
+
+  for (;;)
+    {
+    __syncthreads();
+    if (threadIdx.x == 0) sh_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sh_tile;
+    if (tile >= a.nranges) break;
+    const uint64_t lo = (uint64_t)tile << a.log2B;
+    const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
+
+    // 1. load + split
+    const uint8_t* gin = reinterpret_cast<const uint8_t*>(a.in) + lo * WB;
+    if (WB == 1)
+      {
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) planes[i] = gin[i];
+      }
+    else if ((reinterpret_cast<uintptr_t>(gin) & 15u) == 0)
+      {
+      constexpr int EPV = 16 / WB;                                   // elements per 16-byte vector
+      const uint32_t nvec = cnt / EPV;
+      const uint4* g4 = reinterpret_cast<const uint4*>(gin);
+      for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x)
+        {
+        const uint4 v = __ldg(g4 + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        if (WB == 4)
+          {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) planes[p * pstride + i * 4 + e] = (uint8_t)(w[e] >> (8 * p));
+          }
+        else if (WB == 2)
+          {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            {
+            const uint32_t h = w[e >> 1] >> (16 * (e & 1));
+            planes[0 * pstride + i * 8 + e] = (uint8_t)h;
+            planes[1 * pstride + i * 8 + e] = (uint8_t)(h >> 8);
+            }
+          }
+        else
+          {
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int p = 0; p < 8; ++p) planes[p * pstride + i * 2 + e] = (uint8_t)(w[2 * e + (p >> 2)] >> (8 * (p & 3)));
+          }
+        }
+      for (uint32_t i = nvec * EPV + threadIdx.x; i < cnt; i += blockDim.x)
+        for (int p = 0; p < WB; ++p) planes[p * pstride + i] = gin[(size_t)i * WB + p];
+      }
+    else
+      {
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+        for (int p = 0; p < WB; ++p) planes[p * pstride + i] = gin[(size_t)i * WB + p];
+      }
+    // zero the read-ahead pad so unaligned 32-bit reads past cnt are defined
+    if (threadIdx.x < WB * 16) planes[(threadIdx.x >> 4) * pstride + cnt + (threadIdx.x & 15)] = 0;
+    __syncthreads();
+
+    // 2. compress plane `warp`
+    const uint32_t nbytes = lz4_compress_warp<LZ4_HLOG>(planes + (size_t)warp * pstride, cnt, my_scratch, tables + ((size_t)warp << LZ4_HLOG));
+    if (lane == 0) sh_size[warp] = nbytes;
+    __threadfence_block();
+    __syncthreads();
+
+    // 3. offsets, assembly
+    uint32_t off = 0, agg = 0;
+#pragma unroll
+    for (int w = 0; w < WB; ++w) { const uint32_t s = sh_size[w]; if (w < (int)warp) off += s; agg += s; }
+    if (warp == 0)
+      {
+      const uint64_t excl = lookback_exclusive(a.desc, tile, agg);
+      if (lane == 0)
+        {
+        sh_base = excl;
+        if (tile == a.nranges - 1) { *a.total = excl + agg; store_u64_bytes(a.total_field, excl + agg); }
+        }
+      }
+    __syncthreads();
+    uint8_t* dst = a.payload + sh_base + off;
+    // scratch -> final position (both global; bytes were written by this warp)
+    uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+    if (head > nbytes) head = nbytes;
+    if (lane < head) dst[lane] = __ldcg(my_scratch + lane);
+    const uint32_t nvec = (nbytes - head) >> 4;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(my_scratch + (head & ~3u));
+    const unsigned sh = (head & 3u) * 8u;
+    uint4* dv = reinterpret_cast<uint4*>(dst + head);
+    for (uint32_t i = lane; i < nvec; i += 32)
+      {
+      const uint32_t* s = sw + 4 * i;
+      const uint32_t w0 = __ldcg(s), w1 = __ldcg(s + 1), w2 = __ldcg(s + 2), w3 = __ldcg(s + 3), w4 = __ldcg(s + 4);
+      uint4 o;
+      o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+      o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+      dv[i] = o;
+      }
+    const uint32_t done = head + (nvec << 4);
+    if (done + lane < nbytes) dst[done + lane] = __ldcg(my_scratch + done + lane);
+    if (lane == 0)
+      {
+      uint8_t* sz = a.sizes + 2 * ((uint64_t)tile * WB + warp);
+      sz[0] = (uint8_t)nbytes; sz[1] = (uint8_t)(nbytes >> 8);
+      }
+    }
+  }
+
+// ---------------------------------------------------------------------------------------------
+// K6: per-block LZ4 decode fused with the plane merge (trico_transpose_uint*_soa_to_aos,
+// transpose_aos_to_soa.c:94-147).  CTA = WB warps, tile = one range; warp p decodes plane p
+// into shared memory, then the CTA writes the merged elements with 16-byte stores.
+// ---------------------------------------------------------------------------------------------
+struct Lz4DecodeArgs
+  {
+  const uint8_t* sizes;
+  const uint8_t* payload;
+  uint64_t payload_bytes;
+  uint64_t n;
+  uint32_t nranges;
+  int log2B;
+  void* out;
+  uint64_t* desc;
+  uint32_t* ticket;
+  uint32_t* status;        // set to 1 if any block was malformed
+  };
+
+template <int WB>
+__global__ void __launch_bounds__(WB * 32)
+lz4_decode_kernel(const Lz4DecodeArgs a)
+  {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t B = 1u << a.log2B;
+  const uint32_t pstride = B + 16;
+  uint8_t* planes = smem_raw;
+  __shared__ uint32_t sh_tile;
+  __shared__ uint64_t sh_base;
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+
+  for (;;)
+    {
+    __syncthreads();
+    if (threadIdx.x == 0) sh_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sh_tile;
+    if (tile >= a.nranges) break;
+    const uint64_t lo = (uint64_t)tile << a.log2B;
+    const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
+
+    uint32_t off = 0, agg = 0, mine = 0;
+#pragma unroll
+    for (int w = 0; w < WB; ++w)
+      {
+      const uint8_t* sz = a.sizes + 2 * ((uint64_t)tile * WB + w);
+      const uint32_t s = (uint32_t)sz[0] | ((uint32_t)sz[1] << 8);
+      if (w < (int)warp) off += s;
+      if (w == (int)warp) mine = s;
+      agg += s;
+      }
+    if (warp == 0)
+      {
+      const uint64_t excl = lookback_exclusive(a.desc, tile, agg);
+      if (lane == 0) sh_base = excl;
+      }
+    __syncthreads();
+    const uint64_t start = sh_base + off;
+    uint32_t got = 0xffffffffu;
+    if (start + mine <= a.payload_bytes)
+      got = lz4_decompress_warp<false>(a.payload + start, mine, planes + (size_t)warp * pstride, cnt);
+    if (got != cnt && lane == 0) *a.status = 1;
+    __syncthreads();
+
+    // merge: element i = bytes planes[p][i], p = 0..WB-1 (LSB first)
+    uint8_t* gout = reinterpret_cast<uint8_t*>(a.out) + lo * WB;
+    if (WB == 1)
+      {
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) gout[i] = planes[i];
+      }
+    else if ((reinterpret_cast<uintptr_t>(gout) & 15u) == 0)
+      {
+      constexpr int EPV = 16 / WB;
+      const uint32_t nvec = cnt / EPV;
+      uint4* g4 = reinterpret_cast<uint4*>(gout);
+      for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x)
+        {
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (WB == 4)
+          {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) w[e] |= (uint32_t)planes[p * pstride + i * 4 + e] << (8 * p);
+          }
+        else if (WB == 2)
+          {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            w[e >> 1] |= ((uint32_t)planes[i * 8 + e] | ((uint32_t)planes[pstride + i * 8 + e] << 8)) << (16 * (e & 1));
+          }
+        else
+          {
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int p = 0; p < 8; ++p) w[2 * e + (p >> 2)] |= (uint32_t)planes[p * pstride + i * 2 + e] << (8 * (p & 3));
+          }
+        g4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      for (uint32_t i = nvec * EPV + threadIdx.x; i < cnt; i += blockDim.x)
+        for (int p = 0; p < WB; ++p) gout[(size_t)i * WB + p] = planes[p * pstride + i];
+      }
+    else
+      {
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+        for (int p = 0; p < WB; ++p) gout[(size_t)i * WB + p] = planes[p * pstride + i];
+      }
+    }
+  }
+
+// ---------------------------------------------------------------------------------------------
+// K6L: reference-format planes - ONE LZ4 block per whole plane (trico.c:346, :1101).  One warp per
+// plane decodes serially into a global plane buffer; the merge is a second kernel (planes.cuh).
+// ---------------------------------------------------------------------------------------------
+struct Lz4LegacyDecodeArgs
+  {
+  const uint8_t* src[8];
+  uint32_t src_len[8];
+  uint8_t* planes;         // nplanes buffers of plane_stride bytes
+  uint64_t plane_stride;
+  uint32_t raw_len;
+  uint32_t* status;
+  };
+
+__global__ void __launch_bounds__(32)
+lz4_decode_legacy_kernel(const Lz4LegacyDecodeArgs a)
+  {
+  const unsigned p = blockIdx.x;
+  const uint32_t got = lz4_decompress_warp<true>(a.src[p], a.src_len[p], a.planes + (size_t)p * a.plane_stride, a.raw_len);
+  if (got != a.raw_len && lane_id() == 0) *a.status = 1;
+  }
+
+} // namespace tb200
