@@ -98,7 +98,7 @@ def test_fpc_decode_of_oracle_streams(dev, oracle):
     """the GPU decoder on streams the CPU oracle wrote, including other exponent pairs"""
     for ty in (1, 2, 5, 15):
         data = _synthetic(ty, 5000, 11)
-        for (e1, e2) in ((2, 4), (4, 4), (2, 2), (4, 6), (6, 8)):
+        for (e1, e2) in ((2, 4), (4, 4), (2, 2), (4, 6), (2, 6)):
             for log2c in (6, 9):
                 s = oracle.v1_write_stream(ty, data, 5000, log2c, e1, e2)
                 assert dev.decode_stream(s).tobytes() == data.tobytes(), (ty, e1, e2, log2c)
@@ -108,7 +108,7 @@ def test_fpc_decode_of_oracle_streams(dev, oracle):
 @pytest.mark.parametrize("ty", LZ4_TYPES)
 def test_lz4_streams_valid_and_roundtrip(dev, oracle, golden, ty):
     data, cnt = _stream_input(golden, ty)
-    for log2c in (8, 12, 14, 15):
+    for log2c in (8, 12, 14, 15 if oracle.layout(ty)["wordsize"] < 8 else 13):
         s = dev.encode_stream(ty, data, cnt, log2c)
         # container + every block parse with the CPU oracle
         t, c, arr, used = oracle.v1_read_stream(b"Trco\x01\0\0\0" + s, 8)

@@ -232,6 +232,7 @@ static int write_stream(void* h, int type, const void* data, uint32_t count)
   worker* w = a->w;
   int log2c = codec == 1 ? a->fpc_log2 : a->lz4_log2;
   if (codec == 1 && log2c && ws == 8 && log2c > 11) log2c = 11;
+  if (codec == 2 && log2c && ws == 8 && log2c > 14) log2c = 14;
   if (!log2c) log2c = tb200_default_log2_chunk(type, count);
   const uint64_t nscalars = (uint64_t)count * pc * (codec == 1 ? nc : 1);
   const uint64_t raw_bytes = nscalars * ws;

@@ -155,7 +155,7 @@ extern "C" int tb200_default_log2_chunk(int type, uint32_t count)
   const int codec = tb200_stream_layout(type, &w, &nc, &pc);
   (void)count;
   if (codec == 1) return w == 4 ? 9 : 8;     // 512 floats / 256 doubles per chunk (ratio cost <= 1 %)
-  if (codec == 2) return 14;                 // 16 KiB plane blocks
+  if (codec == 2) return w == 8 ? 13 : 14;   // 16 KiB plane blocks (8 KiB for 8-byte elements: 8 planes share one CTA)
   return 0;
   }
 
@@ -202,7 +202,7 @@ extern "C" int tb200_fpc_encode(tb200_ctx* c, int wordsize, int ncomp, const voi
   {
   CK(cudaSetDevice(c->device));
   if ((wordsize != 4 && wordsize != 8) || ncomp < 1 || ncomp > 3) return fail_msg("tb200_fpc_encode: bad wordsize/ncomp");
-  if (e1 < 2 || e2 < 2 || e1 > 8 || e2 > 8 || (e1 & 1) || (e2 & 1)) return fail_msg("tb200_fpc_encode: chunk exponents must be even, 2..8");
+  if (e1 < 2 || e2 < 2 || e1 > 4 || e2 > 6 || (e1 & 1) || (e2 & 1)) return fail_msg("tb200_fpc_encode: chunk exponents must be even, e1 in 2..4, e2 in 2..6");
   if (log2_chunk < 5 || fpc_chunk_bound(1u << log2_chunk, wordsize) > 65535u) return fail_msg("tb200_fpc_encode: bad chunk size");
   FpcEncodeArgs a;
   a.in = d_in; a.n = n; a.log2S = log2_chunk; a.e1 = e1; a.e2 = e2;
@@ -246,7 +246,7 @@ extern "C" int tb200_fpc_decode(tb200_ctx* c, int wordsize, int ncomp, const uin
   {
   CK(cudaSetDevice(c->device));
   if ((wordsize != 4 && wordsize != 8) || ncomp < 1 || ncomp > 3) return fail_msg("tb200_fpc_decode: bad wordsize/ncomp");
-  if (e1 < 2 || e2 < 2 || e1 > 8 || e2 > 8 || (e1 & 1) || (e2 & 1)) return fail_msg("tb200_fpc_decode: chunk exponents must be even, 2..8");
+  if (e1 < 2 || e2 < 2 || e1 > 4 || e2 > 6 || (e1 & 1) || (e2 & 1)) return fail_msg("tb200_fpc_decode: chunk exponents must be even, e1 in 2..4, e2 in 2..6");
   if (log2_chunk < 5 || log2_chunk > 13) return fail_msg("tb200_fpc_decode: bad chunk size");
   if (n == 0) return 1;
   FpcDecodeArgs a;
@@ -263,7 +263,7 @@ extern "C" int tb200_fpc_decode(tb200_ctx* c, int wordsize, int ncomp, const uin
 // ------------------------------------------------------------------------------------------------
 extern "C" uint64_t tb200_fpc_v0_bound(int wordsize, uint32_t n)
   {
-  return 5 + (uint64_t)fpc_chunk_bound(0, wordsize) + (wordsize == 4 ? (uint64_t)n * 4 + 3 * (((uint64_t)n + 7) / 8) : (uint64_t)n * 8 + ((uint64_t)n + 1) / 2) + 16;
+  return 5 + (wordsize == 4 ? (uint64_t)n * 4 + 3 * (((uint64_t)n + 7) / 8) + 8 : (uint64_t)n * 8 + ((uint64_t)n + 1) / 2 + 2) + 16;
   }
 
 static void norm_exponents(int* e1, int* e2)

@@ -472,7 +472,8 @@ fpc_decode_kernel(const FpcDecodeArgs a)
 
   uint32_t* wrow = win + ((size_t)warp * 32 + lane) * WIN::WORDS;
   uint32_t* wwarp = win + (size_t)warp * 32 * WIN::WORDS;
-  const uint8_t* pay_last = a.payload + ((a.payload_bytes ? a.payload_bytes - 1 : 0) & ~(uint64_t)3);   // last readable word start (payload is 4-aligned or clamped below)
+  // start of the last 32-bit word that still holds a payload byte: window loads are clamped to it
+  const uint8_t* pay_last = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(a.payload) + (a.payload_bytes ? a.payload_bytes - 1 : 0)) & ~(uintptr_t)3);
   W* srow = stagebuf + (size_t)klocal * ROW + c;
   W* gout = reinterpret_cast<W*>(a.out);
 
@@ -483,11 +484,11 @@ fpc_decode_kernel(const FpcDecodeArgs a)
     for (int l = 0; l < 32; ++l)
       {
       const uint64_t p = __shfl_sync(FULL, pos, l);
-      const uint8_t* base = a.payload + (p & ~(uint64_t)3) - ((uintptr_t)a.payload & 3);   // word-aligned address at or below the byte
+      const uint8_t* base = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(a.payload) + p) & ~(uintptr_t)3);   // word-aligned address at or below the byte
       for (int w = lane; w < WIN::WORDS; w += 32)
         {
         const uint8_t* q = base + 4 * w;
-        if (q > pay_last) q = pay_last - ((uintptr_t)pay_last & 3);
+        if (q > pay_last) q = pay_last;
         wwarp[l * WIN::WORDS + w] = *reinterpret_cast<const uint32_t*>(q);
         }
       }

@@ -57,7 +57,7 @@ template <int HLOG, typename DstPtr>
 __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* table)
   {
   const unsigned lane = lane_id();
-  const unsigned gt = lanemask_gt();
+  const unsigned gt = lanemask_gt(), lt = lanemask_lt();
   uint32_t op = 0, anchor = 0;
   if (n >= LZ4_MFLIMIT + 1)
     {
@@ -72,18 +72,37 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
       const bool valid = q <= mflimit;
       const uint32_t seq = valid ? smem_read32(src, q) : 0u;
       const uint32_t h = (seq * 2654435761u) >> (32 - HLOG);
-      const uint32_t cand = table[h];
-      __syncwarp();
-      // deterministic insertion: among lanes with the same bucket the highest position wins
-      const unsigned same = __match_any_sync(FULL, valid ? h : (0x80000000u | lane));
-      if (valid && (same & gt) == 0) table[h] = (uint16_t)q;
-      const bool ok = valid && cand < q && smem_read32(src, cand) == seq;
+      uint32_t cand = table[h];
+      bool ok = valid && cand < q && smem_read32(src, cand) == seq;
+      // repeats closer than the window width are invisible to the table (it is read before this
+      // window is inserted): find them by comparing the 4-byte sequences of the lanes directly
+      const unsigned twins = __match_any_sync(FULL, valid ? seq : (0x5a000000u ^ lane)) & lt & __ballot_sync(FULL, valid);
+      if (valid && twins)
+        {
+        const uint32_t near = p + (31u - (uint32_t)__clz((int)twins));
+        if (!ok || near > cand) { cand = near; ok = true; }
+        }
       const unsigned mask = __ballot_sync(FULL, ok);
+      const int f = mask ? __ffs((int)mask) - 1 : 31;
+      // Insert the scanned positions up to the chosen match only: later ones are scanned again
+      // and must still see their older candidates.  Among lanes sharing a bucket the highest
+      // position wins, so the table (and the output) is deterministic.
+      const bool ins = valid && (int)lane <= f;
+      const unsigned same = __match_any_sync(FULL, ins ? h : (0x80000000u | lane));
+      __syncwarp();
+      if (ins && (same & gt) == 0) table[h] = (uint16_t)q;
       __syncwarp();
       if (mask == 0) { p += 32; continue; }
-      const int f = __ffs((int)mask) - 1;
-      const uint32_t mq = p + (uint32_t)f;
-      const uint32_t mc = __shfl_sync(FULL, cand, f);
+      uint32_t mq = p + (uint32_t)f;
+      uint32_t mc = __shfl_sync(FULL, cand, f);
+      // backward extension over bytes not yet emitted (lz4.c:947-950 does the same serially)
+        {
+        const uint32_t room = min(min(mq - anchor, mc), 32u);
+        const bool eqb = lane < room && src[mq - 1 - lane] == src[mc - 1 - lane];
+        const unsigned neb = ~__ballot_sync(FULL, eqb);
+        const uint32_t back = neb ? (uint32_t)__ffs((int)neb) - 1u : 32u;
+        mq -= back; mc -= back;
+        }
       // forward extension, 32 bytes per step
       uint32_t len = LZ4_MINMATCH;
       for (;;)
@@ -97,6 +116,9 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
         }
       op = lz4_emit(dst, op, src, anchor, mq - anchor, mq - mc, len);
       p = anchor = mq + len;
+      // like lz4.c:1118, remember one position inside the match tail
+      if (lane == 0 && p - 2 <= mflimit) table[(smem_read32(src, p - 2) * 2654435761u) >> (32 - HLOG)] = (uint16_t)(p - 2);
+      __syncwarp();
       }
     }
   op = lz4_emit(dst, op, src, anchor, n - anchor, 0, 0);
