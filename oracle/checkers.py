@@ -5,7 +5,8 @@
                 /root/reference by oracle/Makefile (present wherever that build ran; the .so
                 travels to the GPU box, the sources do not).
 
-Nothing in trico_b200/ imports this module.
+Nothing in trico_b200/ imports this module; only tests/, __graft_entry__.smoke() and bench.py's
+CPU-baseline legs do.
 """
 from __future__ import annotations
 
@@ -15,8 +16,8 @@ import subprocess
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(ORACLE_DIR)
 ORACLE_SO = os.path.join(ORACLE_DIR, "_ref", "libtrico_oracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libtrico_ref.so")
 

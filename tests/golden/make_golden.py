@@ -19,7 +19,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
 from checkers import Ref  # noqa: E402
 
 BUNNY = "/root/reference/trico.tests/data/StanfordBunny.stl"
