@@ -27,6 +27,26 @@ __device__ __forceinline__ uint32_t smem_read32(const uint8_t* base, uint32_t po
   return __funnelshift_r(w[0], w[1], (pos & 3u) * 8u);
   }
 
+// warp copy of n literal bytes src[s..s+n) (shared memory) to dst (any alignment, any space);
+// long runs move as 32-bit words (128 bytes per warp instruction)
+template <typename DstPtr>
+__device__ __forceinline__ void lz4_copy_from_smem(DstPtr dst, const uint8_t* src, uint32_t s, uint32_t n)
+  {
+  const unsigned lane = lane_id();
+  if (n <= 64)
+    {
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[s + i];
+    return;
+    }
+  const uint32_t head = (4u - ((uint32_t)reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+  if (lane < head) dst[lane] = src[s + lane];
+  const uint32_t nw = (n - head) >> 2;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  for (uint32_t i = lane; i < nw; i += 32) dw[i] = smem_read32(src, s + head + 4 * i);
+  const uint32_t done = head + (nw << 2);
+  if (done + lane < n) dst[done + lane] = src[s + done + lane];
+  }
+
 // Emits one sequence (warp-cooperative).  `mlen` = 0 means "last sequence, literals only".
 // Returns the new output position.
 template <typename DstPtr>
@@ -39,7 +59,7 @@ __device__ __forceinline__ uint32_t lz4_emit(DstPtr dst, uint32_t op, const uint
   if (lane == 0) dst[op] = (uint8_t)(((nlit >= 15 ? 15u : nlit) << 4) | (m >= 15 ? 15u : m));
   for (uint32_t i = lane; i < next; i += 32) dst[op + 1 + i] = (i + 1 == next) ? (uint8_t)((nlit - 15) % 255) : (uint8_t)255;
   op += 1 + next;
-  for (uint32_t i = lane; i < nlit; i += 32) dst[op + i] = src[lit_start + i];
+  lz4_copy_from_smem(dst + op, src, lit_start, nlit);
   op += nlit;
   if (mlen)
     {
@@ -51,8 +71,13 @@ __device__ __forceinline__ uint32_t lz4_emit(DstPtr dst, uint32_t op, const uint
   return op;
   }
 
-// Compresses src[0..n) (shared memory, readable 8 bytes past n) into dst.  `table` = HSIZE u16
-// entries of shared memory private to the warp.  n <= 65535.  Returns compressed size.
+constexpr uint32_t LZ4_SRC_PAD = 176;    // zeroed bytes the compressor may read past the block end
+
+// Compresses src[0..n) (shared memory, LZ4_SRC_PAD zero bytes readable past n) into dst.
+// `table` = (1 << HLOG) u16 entries of shared memory private to the warp.  n <= 65535.
+// Greedy single-pass matcher; every lane tests one position per step.  Like the reference
+// (lz4.c:879-909) the scan accelerates over data that does not match: after every 64 failed
+// attempts the distance between tested positions grows by one.
 template <int HLOG, typename DstPtr>
 __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* table)
   {
@@ -65,26 +90,27 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
     __syncwarp();
     const uint32_t mflimit = n - LZ4_MFLIMIT;        // last position where a match may start
     const uint32_t matchlimit = n - LZ4_LASTLITERALS;
-    uint32_t p = 0;
+    uint32_t p = 0, attempts = 0;
     while (p <= mflimit)
       {
-      const uint32_t q = p + lane;
+      const uint32_t stride = 1u + (attempts >> 6);
+      const uint32_t q = p + lane * stride;
       const bool valid = q <= mflimit;
       const uint32_t seq = valid ? smem_read32(src, q) : 0u;
       const uint32_t h = (seq * 2654435761u) >> (32 - HLOG);
       uint32_t cand = table[h];
       bool ok = valid && cand < q && smem_read32(src, cand) == seq;
-      // repeats closer than the window width are invisible to the table (it is read before this
-      // window is inserted): find them by comparing the 4-byte sequences of the lanes directly
+      // repeats inside the window are invisible to the table (it is read before this window is
+      // inserted): find them by comparing the 4-byte sequences of the lanes directly
       const unsigned twins = __match_any_sync(FULL, valid ? seq : (0x5a000000u ^ lane)) & lt & __ballot_sync(FULL, valid);
       if (valid && twins)
         {
-        const uint32_t near = p + (31u - (uint32_t)__clz((int)twins));
+        const uint32_t near = p + (31u - (uint32_t)__clz((int)twins)) * stride;
         if (!ok || near > cand) { cand = near; ok = true; }
         }
       const unsigned mask = __ballot_sync(FULL, ok);
       const int f = mask ? __ffs((int)mask) - 1 : 31;
-      // Insert the scanned positions up to the chosen match only: later ones are scanned again
+      // Insert the tested positions up to the chosen match only: later ones are scanned again
       // and must still see their older candidates.  Among lanes sharing a bucket the highest
       // position wins, so the table (and the output) is deterministic.
       const bool ins = valid && (int)lane <= f;
@@ -92,8 +118,9 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
       __syncwarp();
       if (ins && (same & gt) == 0) table[h] = (uint16_t)q;
       __syncwarp();
-      if (mask == 0) { p += 32; continue; }
-      uint32_t mq = p + (uint32_t)f;
+      if (mask == 0) { p += 32u * stride; attempts += 32; continue; }
+      attempts = 0;
+      uint32_t mq = p + (uint32_t)f * stride;
       uint32_t mc = __shfl_sync(FULL, cand, f);
       // backward extension over bytes not yet emitted (lz4.c:947-950 does the same serially)
         {
@@ -103,17 +130,26 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
         const uint32_t back = neb ? (uint32_t)__ffs((int)neb) - 1u : 32u;
         mq -= back; mc -= back;
         }
-      // forward extension, 32 bytes per step
+      // forward extension, 4 bytes per lane = 128 bytes per step; bytes past the block end are
+      // zero padding and the result is clamped to the last position a match may cover
+      const uint32_t maxlen = matchlimit - mq;
       uint32_t len = LZ4_MINMATCH;
       for (;;)
         {
-        const uint32_t idx = mq + len + lane;
-        const bool eq = idx < matchlimit && src[idx] == src[mc + len + lane];
-        const unsigned ne = __ballot_sync(FULL, !eq);
-        if (ne == 0) { len += 32; continue; }
-        len += (uint32_t)__ffs((int)ne) - 1u;
+        const uint32_t x = smem_read32(src, mq + len + 4 * lane) ^ smem_read32(src, mc + len + 4 * lane);
+        const unsigned ne = __ballot_sync(FULL, x != 0);
+        if (ne == 0)
+          {
+          len += 128;
+          if (len >= maxlen) break;
+          continue;
+          }
+        const int fl = __ffs((int)ne) - 1;
+        const uint32_t xf = __shfl_sync(FULL, x, fl);
+        len += 4u * (uint32_t)fl + (((uint32_t)__ffs((int)xf) - 1u) >> 3);
         break;
         }
+      if (len > maxlen) len = maxlen;
       op = lz4_emit(dst, op, src, anchor, mq - anchor, mq - mc, len);
       p = anchor = mq + len;
       // like lz4.c:1118, remember one position inside the match tail
@@ -125,10 +161,36 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
   return op;
   }
 
-// Warp-cooperative LZ4 block decoder.  src: compressed bytes (global).  dst: output; with
-// DST_GLOBAL the match source is re-read from global memory behind a warp fence (legacy whole-plane
-// blocks), otherwise dst is shared memory.  Returns the number of bytes produced, or 0xffffffff on
-// a malformed block (out-of-range offset / overrun), in which case output is unspecified.
+// copy `n` bytes inside the output buffer from distance `dist` >= n behind (non-overlapping)
+template <bool DST_GLOBAL>
+__device__ __forceinline__ void lz4_copy_back(uint8_t* dst, uint32_t to, uint32_t dist, uint32_t n)
+  {
+  const unsigned lane = lane_id();
+  const uint8_t* ms = dst + to - dist;
+  if (DST_GLOBAL)
+    {
+    for (uint32_t i = lane; i < n; i += 32) dst[to + i] = __ldcg(ms + i);
+    return;
+    }
+  if (n <= 64)
+    {
+    for (uint32_t i = lane; i < n; i += 32) dst[to + i] = ms[i];
+    return;
+    }
+  const uint32_t head = (4u - (to & 3u)) & 3u;         // dst buffers are 4-byte aligned
+  if (lane < head) dst[to + lane] = ms[lane];
+  const uint32_t nw = (n - head) >> 2;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + to + head);
+  const uint32_t sfrom = to - dist + head;
+  for (uint32_t i = lane; i < nw; i += 32) dw[i] = smem_read32(dst, sfrom + 4 * i);
+  const uint32_t done = head + (nw << 2);
+  if (done + lane < n) dst[to + done + lane] = ms[done + lane];
+  }
+
+// Warp-cooperative LZ4 block decoder.  src: compressed bytes (global).  dst: output, 4-byte
+// aligned; with DST_GLOBAL the match source is re-read from global memory behind a warp fence
+// (reference-format whole-plane blocks), otherwise dst is shared memory.  Returns the number of
+// bytes produced, or 0xffffffff on a malformed block (out-of-range offset / overrun).
 template <bool DST_GLOBAL>
 __device__ __forceinline__ uint32_t lz4_decompress_warp(const uint8_t* __restrict__ src, uint32_t src_len,
                                                         uint8_t* dst, uint32_t dst_cap)
@@ -136,6 +198,7 @@ __device__ __forceinline__ uint32_t lz4_decompress_warp(const uint8_t* __restric
   const unsigned lane = lane_id();
   uint32_t ip = 0, op = 0;
   if (src_len == 0) return 0xffffffffu;
+  const uint8_t* src_end = src + src_len;
   for (;;)
     {
     if (ip >= src_len) return 0xffffffffu;
@@ -147,7 +210,28 @@ __device__ __forceinline__ uint32_t lz4_decompress_warp(const uint8_t* __restric
       do { if (ip >= src_len) return 0xffffffffu; b = src[ip++]; lit += b; } while (b == 255);
       }
     if (ip + lit > src_len || op + lit > dst_cap) return 0xffffffffu;
-    for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = src[ip + i];
+    if (lit <= 64)
+      {
+      for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = src[ip + i];
+      }
+    else
+      { // long literal run: 32-bit words, destination aligned, source funnel-shifted
+      const uint32_t head = (4u - (op & 3u)) & 3u;
+      if (lane < head) dst[op + lane] = src[ip + lane];
+      const uint32_t nw = (lit - head) >> 2;
+      const uint8_t* sp = src + ip + head;
+      const uint32_t* sa = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)3);
+      const unsigned sh = ((unsigned)reinterpret_cast<uintptr_t>(sp) & 3u) * 8u;
+      uint32_t* dw = reinterpret_cast<uint32_t*>(dst + op + head);
+      for (uint32_t i = lane; i < nw; i += 32)
+        {
+        const uint32_t w0 = sa[i];
+        const uint32_t w1 = (sh != 0 && reinterpret_cast<const uint8_t*>(sa + i + 1) < src_end) ? sa[i + 1] : 0u;
+        dw[i] = __funnelshift_r(w0, w1, sh);
+        }
+      const uint32_t done = head + (nw << 2);
+      if (done + lane < lit) dst[op + done + lane] = src[ip + done + lane];
+      }
     ip += lit; op += lit;
     if (ip >= src_len) break;                       // last sequence has no match part
     if (ip + 2 > src_len) return 0xffffffffu;
@@ -161,34 +245,22 @@ __device__ __forceinline__ uint32_t lz4_decompress_warp(const uint8_t* __restric
       }
     mlen += LZ4_MINMATCH;
     if (offset == 0 || offset > op || op + mlen > dst_cap) return 0xffffffffu;
-    if (DST_GLOBAL) { __threadfence_block(); }
+    if (DST_GLOBAL) __threadfence_block();
     __syncwarp();                                   // literals of this sequence are visible
-    // Overlapping copy: byte k of the match equals byte (k mod offset) of the `offset` bytes
-    // before op, all of which are already written.
-    const uint8_t* ms = dst + op - offset;
-    if (offset >= mlen || offset >= 32)
+    // Overlapping copy.  The match is periodic with period `offset`, so bytes can be taken from
+    // any multiple of `offset` behind: each pass copies as much as is already written (distance
+    // grows geometrically), every pass is a plain non-overlapping copy.
+    uint32_t copied = 0, dist = offset;
+    while (copied < mlen)
       {
-      // chunks of at most `offset` bytes never read what they write within a step
-      const uint32_t step = offset >= 32 ? 32u : offset;   // offset >= mlen: one pass of <= 32-byte strides is still safe
-      if (offset >= mlen)
-        for (uint32_t i = lane; i < mlen; i += 32) dst[op + i] = DST_GLOBAL ? __ldcg(ms + i) : ms[i];
-      else
-        for (uint32_t base = 0; base < mlen; base += step)
-          {
-          const uint32_t i = base + lane;
-          if (lane < step && i < mlen) dst[op + i] = DST_GLOBAL ? __ldcg(ms + i) : ms[i];
-          if (DST_GLOBAL) __threadfence_block();
-          __syncwarp();
-          }
-      }
-    else
-      {
-      // short period (offset < 32 and < mlen): replicate the period
-      for (uint32_t i = lane; i < mlen; i += 32) dst[op + i] = DST_GLOBAL ? __ldcg(ms + (i % offset)) : ms[i % offset];
+      if (dist < 1024u) dist = ((offset + copied) / offset) * offset;
+      const uint32_t chunk = min(dist, mlen - copied);
+      lz4_copy_back<DST_GLOBAL>(dst, op + copied, dist, chunk);
+      copied += chunk;
+      if (DST_GLOBAL) __threadfence_block();
+      __syncwarp();
       }
     op += mlen;
-    if (DST_GLOBAL) __threadfence_block();
-    __syncwarp();
     }
   return op;
   }
@@ -225,7 +297,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
   {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t B = 1u << a.log2B;
-  const uint32_t pstride = B + 16;                                   // plane buffers padded for read-ahead
+  const uint32_t pstride = B + LZ4_SRC_PAD;                          // plane buffers padded for read-ahead
   uint8_t* planes = smem_raw;                                        // [WB][pstride]
   uint16_t* tables = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WB * pstride);   // [WB][1<<HLOG]
   __shared__ uint32_t sh_tile;
@@ -292,8 +364,8 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
       for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
         for (int p = 0; p < WB; ++p) planes[p * pstride + i] = gin[(size_t)i * WB + p];
       }
-    // zero the read-ahead pad so unaligned 32-bit reads past cnt are defined
-    if (threadIdx.x < WB * 16) planes[(threadIdx.x >> 4) * pstride + cnt + (threadIdx.x & 15)] = 0;
+    // zero the read-ahead pad: the compressor compares up to LZ4_SRC_PAD bytes past cnt
+    for (uint32_t i = threadIdx.x; i < WB * LZ4_SRC_PAD; i += blockDim.x) planes[(i / LZ4_SRC_PAD) * pstride + cnt + (i % LZ4_SRC_PAD)] = 0;
     __syncthreads();
 
     // 2. compress plane `warp`
