@@ -38,4 +38,5 @@ def golden():
     bunny = dict(np.load(os.path.join(here, "bunny_head.npz")))
     with open(os.path.join(here, "bunny_facts.json")) as f:
         facts = json.load(f)
-    return {"kat": kat, "bunny": bunny, "facts": facts}
+    full = dict(np.load(os.path.join(here, "bunny_full.npz")))
+    return {"kat": kat, "bunny": bunny, "facts": facts, "bunny_full": full}

@@ -92,6 +92,9 @@ def main():
     facts["vertices_sha1"] = hashlib.sha1(v.tobytes()).hexdigest()
     facts["triangles_sha1"] = hashlib.sha1(t.tobytes()).hexdigest()
 
+    # the whole bunny as the reference sees it, with the reference's own archive (config C1)
+    np.savez_compressed(os.path.join(HERE, "bunny_full.npz"), vertices=v, triangles=t, v0_archive=np.frombuffer(full, np.uint8))
+
     hv, ht = v[:4096].copy(), t[20000:24096].copy()
     n = 4096
     streams = {

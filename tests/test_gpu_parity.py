@@ -350,3 +350,27 @@ def test_medium_mesh_roundtrip_properties(dev, oracle):
     assert dev.decode_stream(s3).tobytes() == t.tobytes()
     ratio = (v.nbytes + t.nbytes) / (len(s) + len(s3))
     assert ratio > 2.0
+
+
+# ------------------------------------------------------------------------ config C1: the bunny
+def test_c1_bunny_against_reference_archive(ours, oracle, golden):
+    """BASELINE config[0]: the reference's bundled StanfordBunny.stl (after its own STL de-dup).
+    The reference's archive (584,613 bytes, md5 pinned in bunny_facts.json) decodes bit-exactly on
+    the GPU legacy path; our own archive of the same mesh is within 5 % of its size."""
+    import hashlib
+    full = golden["bunny_full"]
+    v, t, ref_blob = full["vertices"], full["triangles"], full["v0_archive"].tobytes()
+    assert len(ref_blob) == golden["facts"]["archive_bytes"] == 584613
+    assert hashlib.md5(ref_blob).hexdigest() == golden["facts"]["archive_md5"]
+    version, dec = ours.decode(ref_blob, oracle)
+    assert version == 0
+    assert dec[0][2].tobytes() == v.tobytes() and dec[1][2].tobytes() == t.tobytes()
+    mine = ours.encode([(1, v, v.shape[0]), (3, t, t.shape[0])])
+    _, back = ours.decode(mine, oracle)
+    assert back[0][2].tobytes() == v.tobytes() and back[1][2].tobytes() == t.tobytes()
+    _, cpu = oracle.read_archive(mine)
+    assert cpu[0][2].tobytes() == v.tobytes() and cpu[1][2].tobytes() == t.tobytes()
+    ratio_ref = (v.nbytes + t.nbytes) / len(ref_blob)
+    ratio_ours = (v.nbytes + t.nbytes) / len(mine)
+    print(f"C1 bunny: reference {len(ref_blob)} B (ratio {ratio_ref:.4f}), ours {len(mine)} B (ratio {ratio_ours:.4f}, {100 * (ratio_ours / ratio_ref - 1):+.2f} %)")
+    assert ratio_ours >= 0.95 * ratio_ref

@@ -101,6 +101,57 @@ static int ensure(uint8_t** buf, uint64_t* cap, uint64_t need, worker* w)
   }
 
 /* ------------------------------------------------------------------------------------------
+ * Host buffers of writable archives.  The reference grows a malloc'd buffer with realloc
+ * (trico.c:31-47); here the buffer is page-locked so the device can DMA the finished stream
+ * straight into it, and closed archives park their buffer in a small pool (page-locking is
+ * expensive, archives are usually written in a loop).  Without a CUDA device page-locking fails
+ * and plain malloc is used, so an empty archive can still be created and inspected.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint8_t* p; uint64_t cap; int pinned; } hostbuf;
+#define POOL_SLOTS 8
+static hostbuf g_pool[POOL_SLOTS];
+static uint64_t g_pool_bytes = 0;
+#define POOL_MAX_BYTES (8ull << 30)
+
+static hostbuf hostbuf_get(uint64_t need)
+  {
+  hostbuf b = {NULL, 0, 0};
+  pthread_mutex_lock(&g_lock);
+  int best = -1;
+  for (int i = 0; i < POOL_SLOTS; ++i)
+    if (g_pool[i].p && g_pool[i].cap >= need && (best < 0 || g_pool[i].cap < g_pool[best].cap)) best = i;
+  if (best >= 0) { b = g_pool[best]; g_pool[best].p = NULL; g_pool_bytes -= b.cap; }
+  pthread_mutex_unlock(&g_lock);
+  if (b.p) return b;
+  const uint64_t cap = need ? need : 1;
+  if (tb200_device_count() > 0 && cap >= (64u << 10))
+    {
+    b.p = (uint8_t*)tb200_host_alloc_pinned(cap);
+    b.pinned = b.p != NULL;
+    }
+  if (!b.p) { b.p = (uint8_t*)malloc(cap); b.pinned = 0; }
+  b.cap = b.p ? cap : 0;
+  return b;
+  }
+
+static void hostbuf_put(hostbuf b)
+  {
+  if (!b.p) return;
+  if (b.pinned)
+    {
+    pthread_mutex_lock(&g_lock);
+    int slot = -1;
+    if (g_pool_bytes + b.cap <= POOL_MAX_BYTES)
+      for (int i = 0; i < POOL_SLOTS; ++i) if (!g_pool[i].p) { slot = i; break; }
+    if (slot >= 0) { g_pool[slot] = b; g_pool_bytes += b.cap; }
+    pthread_mutex_unlock(&g_lock);
+    if (slot >= 0) return;
+    tb200_host_free_pinned(b.p);
+    }
+  else free(b.p);
+  }
+
+/* ------------------------------------------------------------------------------------------
  * archive object (trico.c:12-24)
  * ------------------------------------------------------------------------------------------ */
 typedef struct
@@ -108,7 +159,7 @@ typedef struct
   int writable;
   uint32_t version;
   /* writer: growable host buffer */
-  uint8_t* buffer; uint64_t size; uint64_t cap;
+  uint8_t* buffer; uint64_t size; uint64_t cap; int buffer_pinned;
   /* reader: borrowed bytes (host or device) */
   const uint8_t* data; uint64_t data_size; uint64_t pos;
   int data_on_device;
@@ -123,9 +174,12 @@ static int buffer_reserve(archive* a, uint64_t extra)
   if (a->size + extra <= a->cap) return 1;
   uint64_t want = a->size + extra;
   if (want < a->cap * 2) want = a->cap * 2;
-  uint8_t* p = (uint8_t*)realloc(a->buffer, want ? want : 1);
-  if (!p) return 0;                      /* trico.c:40 */
-  a->buffer = p; a->cap = want;
+  hostbuf nb = hostbuf_get(want);
+  if (!nb.p) return 0;                   /* trico.c:40 */
+  if (a->size) memcpy(nb.p, a->buffer, a->size);
+  hostbuf old = {a->buffer, a->cap, a->buffer_pinned};
+  hostbuf_put(old);
+  a->buffer = nb.p; a->cap = nb.cap; a->buffer_pinned = nb.pinned;
   return 1;
   }
 
@@ -155,9 +209,9 @@ void* trico_open_archive_for_writing(uint64_t initial_buffer_size)
   archive* a = (archive*)calloc(1, sizeof(archive));
   if (!a) return NULL;
   a->writable = 1;
-  a->cap = initial_buffer_size;
-  a->buffer = (uint8_t*)malloc(initial_buffer_size ? initial_buffer_size : 1);
-  if (!a->buffer || !buffer_reserve(a, 8)) { free(a->buffer); free(a); return NULL; }
+  hostbuf b = hostbuf_get(initial_buffer_size < 8 ? 8 : initial_buffer_size);
+  if (!b.p) { free(a); return NULL; }    /* trico.c:141-145 */
+  a->buffer = b.p; a->cap = b.cap; a->buffer_pinned = b.pinned;
   put32(a->buffer, TRICO_MAGIC);         /* trico.c:90-98 */
   put32(a->buffer + 4, 0);               /* version 0 until a chunked stream is appended */
   a->size = 8;
@@ -186,7 +240,8 @@ void trico_close_archive(void* h)
   archive* a = (archive*)h;
   if (!a) return;
   if (a->w) { tb200_ctx_sync(a->w->ctx); worker_release(a->w); }
-  free(a->buffer);
+  hostbuf hb = {a->buffer, a->cap, a->buffer_pinned};
+  hostbuf_put(hb);
   free(a);
   }
 

@@ -479,7 +479,8 @@ fpc_decode_kernel(const FpcDecodeArgs a)
 
   for (uint32_t i0 = 0; i0 < cnt0; i0 += SB)
     {
-    // a. refresh the windows of all 32 lanes of this warp (coalesced 4-byte loads)
+    // a. refresh the windows of all 32 lanes of this warp: coalesced 4-byte cp.async copies
+    //    (global -> shared without a register round trip, all in flight at once)
 #pragma unroll 4
     for (int l = 0; l < 32; ++l)
       {
@@ -489,9 +490,14 @@ fpc_decode_kernel(const FpcDecodeArgs a)
         {
         const uint8_t* q = base + 4 * w;
         if (q > pay_last) q = pay_last;
-        wwarp[l * WIN::WORDS + w] = *reinterpret_cast<const uint32_t*>(q);
+        const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(wwarp + l * WIN::WORDS + w);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(saddr), "l"(q) : "memory");
         }
       }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // pull the bytes this lane will want next time towards L2 while the copies land
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(a.payload + (pos + WIN::BYTES + 64 < a.payload_bytes ? pos + WIN::BYTES + 64 : pos)));
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 
     // b. decode up to SB values of this lane's chunk
