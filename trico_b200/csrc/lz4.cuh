@@ -268,151 +268,186 @@ __device__ __forceinline__ uint32_t lz4_decompress_warp(const uint8_t* __restric
 // ---------------------------------------------------------------------------------------------
 // K2 + K5: byte-plane split (trico_transpose_uint{16,32,64}_aos_to_soa,
 // transpose_aos_to_soa.c:84-147) fused with per-plane-block LZ4 compression and the assembly.
-// Persistent CTAs of WB warps (WB = element bytes).  Per tile (= one range of B elements):
-//   1. coalesced 16-byte loads of the AoS elements, byte planes written to shared memory
-//   2. warp p compresses plane p into the CTA's scratch slot (global, reused -> L2 resident)
-//   3. sizes -> look-back over tiles -> warp p copies its block to the final offset.
+//
+// Two kernels.  lz4_encode_kernel: every WARP is independent (no barrier, no ordering): persistent
+// warps pull chunks g = (range k, plane p), g = k*WB + p, from an atomic ticket;
+//   1. the warp reads the range's AoS elements with coalesced 16-byte loads and keeps byte p of
+//      every element (consecutive tickets = the planes of one range, taken at about the same
+//      time, so the re-reads are L1/L2 hits and DRAM sees the range once)
+//   2. it compresses its plane block into the chunk's own scratch slot and records the size.
+// lz4_assemble_kernel: block scan of the sizes + decoupled look-back over tiles of 256 chunks,
+// then every block is copied to its final offset (only compressed bytes move twice).
 // ---------------------------------------------------------------------------------------------
 struct Lz4EncodeArgs
   {
   const void* in;          // device, n elements of WB bytes
   uint64_t n;
-  uint32_t nranges;        // == ntiles
+  uint32_t nranges;
   int log2B;
   uint8_t* sizes;          // u16 LE [nranges * WB]
   uint8_t* payload;
   uint8_t* total_field;
   uint64_t* total;
-  uint8_t* scratch;        // gridDim.x * WB * slot bytes
+  uint8_t* scratch;        // one slot per chunk
   uint32_t slot;           // bytes per scratch slot (>= lz4_block_bound(B), multiple of 16)
-  uint64_t* desc;
-  uint32_t* ticket;
+  uint64_t* desc;          // look-back descriptors of the assemble kernel, zeroed
+  uint32_t* ticket;        // chunk ticket, zeroed
   };
 
 constexpr int LZ4_HLOG = 12;     // 4096 u16 entries = 8 KiB per warp
+template <int WB> struct Lz4Cta { static constexpr int WARPS = WB > 4 ? WB : 4; };
+
+// keeps byte `p` of every WB-byte element of one 16-byte vector; returns them packed LSB first
+template <int WB>
+__device__ __forceinline__ uint32_t plane_bytes(const uint4 v, uint32_t p)
+  {
+  if (WB == 4)
+    {
+    const uint32_t sel = p | ((4u + p) << 4);                       // byte p of the first, byte p of the second operand
+    const uint32_t lo = __byte_perm(v.x, v.y, sel), hi = __byte_perm(v.z, v.w, sel);
+    return __byte_perm(lo, hi, 0x5410);
+    }
+  if (WB == 2)
+    { // 8 elements -> this returns the first four; see plane_bytes_hi for the rest
+    const uint32_t sel = p | ((2u + p) << 4) | ((4u + p) << 8) | ((6u + p) << 12);
+    return __byte_perm(v.x, v.y, sel);
+    }
+  // WB == 8: two elements
+  const uint32_t a = p < 4 ? v.x : v.y, b = p < 4 ? v.z : v.w;
+  return ((a >> (8 * (p & 3))) & 0xffu) | (((b >> (8 * (p & 3))) & 0xffu) << 8);
+  }
 
 template <int WB>
-__global__ void __launch_bounds__(WB * 32)
+__global__ void __launch_bounds__(Lz4Cta<WB>::WARPS * 32)
 lz4_encode_kernel(const Lz4EncodeArgs a)
   {
+  constexpr int WARPS = Lz4Cta<WB>::WARPS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t B = 1u << a.log2B;
-  const uint32_t pstride = B + LZ4_SRC_PAD;                          // plane buffers padded for read-ahead
-  uint8_t* planes = smem_raw;                                        // [WB][pstride]
-  uint16_t* tables = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WB * pstride);   // [WB][1<<HLOG]
-  __shared__ uint32_t sh_tile;
-  __shared__ uint32_t sh_size[WB];
-  __shared__ uint64_t sh_base;
+  const uint32_t pstride = B + LZ4_SRC_PAD;                          // block buffer padded for read-ahead
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-  uint8_t* my_scratch = a.scratch + ((size_t)blockIdx.x * WB + warp) * a.slot;
+  uint8_t* buf = smem_raw + (size_t)warp * pstride;
+  uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WARPS * pstride) + ((size_t)warp << LZ4_HLOG);
+  const uint64_t nchunks = (uint64_t)a.nranges * WB;
 
   for (;;)
     {
-    __syncthreads();
-    if (threadIdx.x == 0) sh_tile = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = sh_tile;
-    if (tile >= a.nranges) break;
-    const uint64_t lo = (uint64_t)tile << a.log2B;
+    uint32_t g32 = 0;
+    if (lane == 0) g32 = atomicAdd(a.ticket, 1u);
+    const uint64_t g = __shfl_sync(FULL, g32, 0);
+    if (g >= nchunks) break;
+    const uint64_t k = g / WB;
+    const uint32_t p = (uint32_t)(g % WB);
+    const uint64_t lo = k << a.log2B;
     const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
 
-    // 1. load + split
+    // 1. plane p of range k -> buf
     const uint8_t* gin = reinterpret_cast<const uint8_t*>(a.in) + lo * WB;
-    if (WB == 1)
-      {
-      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) planes[i] = gin[i];
-      }
-    else if ((reinterpret_cast<uintptr_t>(gin) & 15u) == 0)
+    if ((reinterpret_cast<uintptr_t>(gin) & 15u) == 0)
       {
       constexpr int EPV = 16 / WB;                                   // elements per 16-byte vector
       const uint32_t nvec = cnt / EPV;
       const uint4* g4 = reinterpret_cast<const uint4*>(gin);
-      for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x)
+#pragma unroll 8
+      for (uint32_t i = lane; i < nvec; i += 32)
         {
         const uint4 v = __ldg(g4 + i);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        if (WB == 4)
-          {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int p = 0; p < 4; ++p) planes[p * pstride + i * 4 + e] = (uint8_t)(w[e] >> (8 * p));
-          }
+        if (WB == 1) reinterpret_cast<uint4*>(buf)[i] = v;
+        else if (WB == 4) reinterpret_cast<uint32_t*>(buf)[i] = plane_bytes<4>(v, p);
         else if (WB == 2)
           {
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            {
-            const uint32_t h = w[e >> 1] >> (16 * (e & 1));
-            planes[0 * pstride + i * 8 + e] = (uint8_t)h;
-            planes[1 * pstride + i * 8 + e] = (uint8_t)(h >> 8);
-            }
+          const uint32_t sel = p | ((2u + p) << 4) | ((4u + p) << 8) | ((6u + p) << 12);
+          reinterpret_cast<uint2*>(buf)[i] = make_uint2(__byte_perm(v.x, v.y, sel), __byte_perm(v.z, v.w, sel));
           }
-        else
-          {
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-#pragma unroll
-            for (int p = 0; p < 8; ++p) planes[p * pstride + i * 2 + e] = (uint8_t)(w[2 * e + (p >> 2)] >> (8 * (p & 3)));
-          }
+        else reinterpret_cast<uint16_t*>(buf)[i] = (uint16_t)plane_bytes<8>(v, p);
         }
-      for (uint32_t i = nvec * EPV + threadIdx.x; i < cnt; i += blockDim.x)
-        for (int p = 0; p < WB; ++p) planes[p * pstride + i] = gin[(size_t)i * WB + p];
+      for (uint32_t i = nvec * EPV + lane; i < cnt; i += 32) buf[i] = gin[(size_t)i * WB + p];
       }
     else
-      {
-      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
-        for (int p = 0; p < WB; ++p) planes[p * pstride + i] = gin[(size_t)i * WB + p];
-      }
+      for (uint32_t i = lane; i < cnt; i += 32) buf[i] = gin[(size_t)i * WB + p];
     // zero the read-ahead pad: the compressor compares up to LZ4_SRC_PAD bytes past cnt
-    for (uint32_t i = threadIdx.x; i < WB * LZ4_SRC_PAD; i += blockDim.x) planes[(i / LZ4_SRC_PAD) * pstride + cnt + (i % LZ4_SRC_PAD)] = 0;
-    __syncthreads();
+    for (uint32_t i = lane; i < LZ4_SRC_PAD; i += 32) buf[cnt + i] = 0;
+    __syncwarp();
 
-    // 2. compress plane `warp`
-    const uint32_t nbytes = lz4_compress_warp<LZ4_HLOG>(planes + (size_t)warp * pstride, cnt, my_scratch, tables + ((size_t)warp << LZ4_HLOG));
-    if (lane == 0) sh_size[warp] = nbytes;
-    __threadfence_block();
-    __syncthreads();
-
-    // 3. offsets, assembly
-    uint32_t off = 0, agg = 0;
-#pragma unroll
-    for (int w = 0; w < WB; ++w) { const uint32_t s = sh_size[w]; if (w < (int)warp) off += s; agg += s; }
-    if (warp == 0)
+    // 2. compress into this chunk's slot
+    const uint32_t nbytes = lz4_compress_warp<LZ4_HLOG>(buf, cnt, a.scratch + g * a.slot, table);
+    if (lane == 0)
       {
-      const uint64_t excl = lookback_exclusive(a.desc, tile, agg);
-      if (lane == 0)
-        {
-        sh_base = excl;
-        if (tile == a.nranges - 1) { *a.total = excl + agg; store_u64_bytes(a.total_field, excl + agg); }
-        }
+      uint8_t* sz = a.sizes + 2 * g;
+      sz[0] = (uint8_t)nbytes; sz[1] = (uint8_t)(nbytes >> 8);
       }
-    __syncthreads();
-    uint8_t* dst = a.payload + sh_base + off;
-    // scratch -> final position (both global; bytes were written by this warp)
+    __syncwarp();
+    }
+  }
+
+// Assembly: chunk g's block sits at scratch + g*slot with its size in sizes[g]; tiles of 256
+// chunks take their base from a look-back over tile totals (all known up front, so no waiting).
+constexpr int LZ4_ASM_THREADS = 256;
+
+__global__ void __launch_bounds__(LZ4_ASM_THREADS)
+lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
+  {
+  __shared__ uint32_t sh_off[LZ4_ASM_THREADS];
+  __shared__ uint32_t sh_sz[LZ4_ASM_THREADS];
+  __shared__ uint32_t sh_wsum[LZ4_ASM_THREADS / 32];
+  __shared__ uint64_t sh_base;
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t tile = blockIdx.x;
+  const uint64_t g0 = (uint64_t)tile * LZ4_ASM_THREADS;
+  uint32_t mysz = 0;
+  if (g0 + threadIdx.x < nchunks)
+    {
+    const uint8_t* sz = a.sizes + 2 * (g0 + threadIdx.x);
+    mysz = (uint32_t)sz[0] | ((uint32_t)sz[1] << 8);
+    }
+  uint32_t incl = mysz;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    {
+    const uint32_t up = __shfl_up_sync(FULL, incl, o);
+    if (lane >= (unsigned)o) incl += up;
+    }
+  if (lane == 31) sh_wsum[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0, tsum = 0;
+#pragma unroll
+  for (int w = 0; w < LZ4_ASM_THREADS / 32; ++w) { const uint32_t t = sh_wsum[w]; if (w < (int)warp) wbase += t; tsum += t; }
+  sh_off[threadIdx.x] = wbase + incl - mysz;
+  sh_sz[threadIdx.x] = mysz;
+  if (warp == 0)
+    {
+    const uint64_t excl = lookback_exclusive(a.desc, tile, tsum);
+    if (lane == 0)
+      {
+      sh_base = excl;
+      if (tile == gridDim.x - 1) { *a.total = excl + tsum; store_u64_bytes(a.total_field, excl + tsum); }
+      }
+    }
+  __syncthreads();
+  for (uint32_t c = warp; c < LZ4_ASM_THREADS && g0 + c < nchunks; c += LZ4_ASM_THREADS / 32)
+    {
+    const uint32_t nbytes = sh_sz[c];
+    const uint8_t* src = a.scratch + (g0 + c) * a.slot;                  // 16-byte aligned
+    uint8_t* dst = a.payload + sh_base + sh_off[c];
     uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
     if (head > nbytes) head = nbytes;
-    if (lane < head) dst[lane] = __ldcg(my_scratch + lane);
+    if (lane < head) dst[lane] = src[lane];
     const uint32_t nvec = (nbytes - head) >> 4;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(my_scratch + (head & ~3u));
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(src + (head & ~3u));
     const unsigned sh = (head & 3u) * 8u;
     uint4* dv = reinterpret_cast<uint4*>(dst + head);
+#pragma unroll 4
     for (uint32_t i = lane; i < nvec; i += 32)
       {
       const uint32_t* s = sw + 4 * i;
-      const uint32_t w0 = __ldcg(s), w1 = __ldcg(s + 1), w2 = __ldcg(s + 2), w3 = __ldcg(s + 3), w4 = __ldcg(s + 4);
+      const uint32_t w0 = s[0], w1 = s[1], w2 = s[2], w3 = s[3], w4 = s[4];
       uint4 o;
       o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
       o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
       dv[i] = o;
       }
     const uint32_t done = head + (nvec << 4);
-    if (done + lane < nbytes) dst[done + lane] = __ldcg(my_scratch + done + lane);
-    if (lane == 0)
-      {
-      uint8_t* sz = a.sizes + 2 * ((uint64_t)tile * WB + warp);
-      sz[0] = (uint8_t)nbytes; sz[1] = (uint8_t)(nbytes >> 8);
-      }
+    if (done + lane < nbytes) dst[done + lane] = src[done + lane];
     }
   }
 
