@@ -275,7 +275,7 @@ __device__ __forceinline__ uint32_t lz4_decompress_warp(const uint8_t* __restric
 //      every element (consecutive tickets = the planes of one range, taken at about the same
 //      time, so the re-reads are L1/L2 hits and DRAM sees the range once)
 //   2. it compresses its plane block into the chunk's own scratch slot and records the size.
-// lz4_assemble_kernel: block scan of the sizes + decoupled look-back over tiles of 256 chunks,
+// lz4_assemble_kernel: block scan of the sizes + decoupled look-back over tiles of 64 chunks,
 // then every block is copied to its final offset (only compressed bytes move twice).
 // ---------------------------------------------------------------------------------------------
 struct Lz4EncodeArgs
@@ -330,26 +330,67 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
   uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WARPS * pstride) + ((size_t)warp << LZ4_HLOG);
   const uint64_t nchunks = (uint64_t)a.nranges * WB;
 
-  for (;;)
+  // tickets are taken one chunk ahead so the next range can be pulled towards L2 while this
+  // chunk is being compressed
+  uint32_t t32 = 0;
+  if (lane == 0) t32 = atomicAdd(a.ticket, 1u);
+  uint64_t g = __shfl_sync(FULL, t32, 0);
+  while (g < nchunks)
     {
-    uint32_t g32 = 0;
-    if (lane == 0) g32 = atomicAdd(a.ticket, 1u);
-    const uint64_t g = __shfl_sync(FULL, g32, 0);
-    if (g >= nchunks) break;
+    if (lane == 0) t32 = atomicAdd(a.ticket, 1u);
+    const uint64_t gnext = __shfl_sync(FULL, t32, 0);
+    if (gnext < nchunks)
+      {
+      const uint8_t* nx = reinterpret_cast<const uint8_t*>(a.in) + ((gnext / WB) << a.log2B) * WB;
+      const uint64_t lim = a.n * WB;
+      for (uint32_t o = lane * 128u; o < B * WB; o += 32u * 128u)
+        if (((gnext / WB) << a.log2B) * WB + o < lim) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + o));
+      }
     const uint64_t k = g / WB;
     const uint32_t p = (uint32_t)(g % WB);
     const uint64_t lo = k << a.log2B;
     const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
 
-    // 1. plane p of range k -> buf
+    // 1. plane p of range k -> buf (loads of the next batch are in flight while this one is split)
     const uint8_t* gin = reinterpret_cast<const uint8_t*>(a.in) + lo * WB;
     if ((reinterpret_cast<uintptr_t>(gin) & 15u) == 0)
       {
       constexpr int EPV = 16 / WB;                                   // elements per 16-byte vector
+      constexpr int UN = 8;
       const uint32_t nvec = cnt / EPV;
       const uint4* g4 = reinterpret_cast<const uint4*>(gin);
-#pragma unroll 8
-      for (uint32_t i = lane; i < nvec; i += 32)
+      const uint32_t nfull = nvec / (32 * UN);                       // whole batches of UN vectors per lane
+      uint4 cur[UN], nxt[UN];
+      if (nfull)
+        {
+#pragma unroll
+        for (int u = 0; u < UN; ++u) cur[u] = __ldg(g4 + lane + 32 * u);
+        }
+      for (uint32_t bidx = 0; bidx < nfull; ++bidx)
+        {
+        if (bidx + 1 < nfull)
+          {
+#pragma unroll
+          for (int u = 0; u < UN; ++u) nxt[u] = __ldg(g4 + (bidx + 1) * 32 * UN + lane + 32 * u);
+          }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+          {
+          const uint32_t i = bidx * 32 * UN + lane + 32 * u;
+          const uint4 v = cur[u];
+          if (WB == 1) reinterpret_cast<uint4*>(buf)[i] = v;
+          else if (WB == 4) reinterpret_cast<uint32_t*>(buf)[i] = plane_bytes<4>(v, p);
+          else if (WB == 2)
+            {
+            const uint32_t sel = p | ((2u + p) << 4) | ((4u + p) << 8) | ((6u + p) << 12);
+            reinterpret_cast<uint2*>(buf)[i] = make_uint2(__byte_perm(v.x, v.y, sel), __byte_perm(v.z, v.w, sel));
+            }
+          else reinterpret_cast<uint16_t*>(buf)[i] = (uint16_t)plane_bytes<8>(v, p);
+          }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) cur[u] = nxt[u];
+        }
+      for (uint32_t i = nfull * 32 * UN + lane; i < nvec; i += 32)
         {
         const uint4 v = __ldg(g4 + i);
         if (WB == 1) reinterpret_cast<uint4*>(buf)[i] = v;
@@ -377,12 +418,13 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
       sz[0] = (uint8_t)nbytes; sz[1] = (uint8_t)(nbytes >> 8);
       }
     __syncwarp();
+    g = gnext;
     }
   }
 
-// Assembly: chunk g's block sits at scratch + g*slot with its size in sizes[g]; tiles of 256
+// Assembly: chunk g's block sits at scratch + g*slot with its size in sizes[g]; tiles of 64
 // chunks take their base from a look-back over tile totals (all known up front, so no waiting).
-constexpr int LZ4_ASM_THREADS = 256;
+constexpr int LZ4_ASM_THREADS = 64;
 
 __global__ void __launch_bounds__(LZ4_ASM_THREADS)
 lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
