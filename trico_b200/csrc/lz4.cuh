@@ -177,7 +177,7 @@ __device__ __forceinline__ void lz4_copy_back(uint8_t* dst, uint32_t to, uint32_
     for (uint32_t i = lane; i < n; i += 32) dst[to + i] = ms[i];
     return;
     }
-  const uint32_t head = (4u - (to & 3u)) & 3u;         // dst buffers are 4-byte aligned
+  const uint32_t head = (4u - (to & 3u)) & 3u;         // shared-memory dst buffers are 16-byte aligned
   if (lane < head) dst[to + lane] = ms[lane];
   const uint32_t nw = (n - head) >> 2;
   uint32_t* dw = reinterpret_cast<uint32_t*>(dst + to + head);
@@ -215,21 +215,38 @@ __device__ __forceinline__ uint32_t lz4_decompress_warp(const uint8_t* __restric
       for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = src[ip + i];
       }
     else
-      { // long literal run: 32-bit words, destination aligned, source funnel-shifted
-      const uint32_t head = (4u - (op & 3u)) & 3u;
+      { // long literal run: 16-byte stores to the aligned destination, source words funnel-shifted;
+        // four vectors per lane are loaded before any is stored so the global latency overlaps
+      const uint32_t head = (16u - ((uint32_t)reinterpret_cast<uintptr_t>(dst + op) & 15u)) & 15u;
       if (lane < head) dst[op + lane] = src[ip + lane];
-      const uint32_t nw = (lit - head) >> 2;
+      const uint32_t nv = (lit - head) >> 4;
       const uint8_t* sp = src + ip + head;
       const uint32_t* sa = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)3);
       const unsigned sh = ((unsigned)reinterpret_cast<uintptr_t>(sp) & 3u) * 8u;
-      uint32_t* dw = reinterpret_cast<uint32_t*>(dst + op + head);
-      for (uint32_t i = lane; i < nw; i += 32)
+      const uint32_t* s_last = reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(src_end) - 1) & ~(uintptr_t)3);   // last word holding a source byte
+      uint4* dv = reinterpret_cast<uint4*>(dst + op + head);
+      constexpr int UN = 4;
+      for (uint32_t i0 = 0; i0 < nv; i0 += 32 * UN)
         {
-        const uint32_t w0 = sa[i];
-        const uint32_t w1 = (sh != 0 && reinterpret_cast<const uint8_t*>(sa + i + 1) < src_end) ? sa[i + 1] : 0u;
-        dw[i] = __funnelshift_r(w0, w1, sh);
+        uint32_t w[UN][5];
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+          {
+          const uint32_t i = i0 + lane + 32 * u;
+          const uint32_t* s = sa + 4 * (i < nv ? i : 0);
+#pragma unroll
+          for (int j = 0; j < 5; ++j) { const uint32_t* q = s + j; w[u][j] = *(q <= s_last ? q : s_last); }
+          }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+          {
+          const uint32_t i = i0 + lane + 32 * u;
+          if (i < nv)
+            dv[i] = make_uint4(__funnelshift_r(w[u][0], w[u][1], sh), __funnelshift_r(w[u][1], w[u][2], sh),
+                               __funnelshift_r(w[u][2], w[u][3], sh), __funnelshift_r(w[u][3], w[u][4], sh));
+          }
         }
-      const uint32_t done = head + (nw << 2);
+      const uint32_t done = head + (nv << 4);
       if (done + lane < lit) dst[op + done + lane] = src[ip + done + lane];
       }
     ip += lit; op += lit;
@@ -248,15 +265,33 @@ __device__ __forceinline__ uint32_t lz4_decompress_warp(const uint8_t* __restric
     if (DST_GLOBAL) __threadfence_block();
     __syncwarp();                                   // literals of this sequence are visible
     // Overlapping copy.  The match is periodic with period `offset`, so bytes can be taken from
-    // any multiple of `offset` behind: each pass copies as much as is already written (distance
-    // grows geometrically), every pass is a plain non-overlapping copy.
+    // any multiple of `offset` behind.  A short period is first expanded to 128 bytes in one
+    // step (lane l writes bytes 4l..4l+3 of the pattern); after that every pass copies as much
+    // as is already written - the distance doubles, every pass is a plain non-overlapping copy.
     uint32_t copied = 0, dist = offset;
+    if (!DST_GLOBAL && offset < 32u && mlen > offset)
+      {
+      const uint32_t n0 = min(mlen, 128u);
+      const uint32_t inv = (65536u + offset - 1u) / offset;
+      const uint8_t* ms = dst + op - offset;
+      uint32_t r = 4u * lane;
+      r -= offset * ((r * inv) >> 16);                        // (4*lane) mod offset
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j)
+        {
+        if (4u * lane + j < n0) dst[op + 4u * lane + j] = ms[r];
+        r = (r + 1u == offset) ? 0u : r + 1u;
+        }
+      copied = n0;
+      dist = ((offset + copied) / offset) * offset;           // largest multiple of the period now available
+      __syncwarp();
+      }
     while (copied < mlen)
       {
-      if (dist < 1024u) dist = ((offset + copied) / offset) * offset;
       const uint32_t chunk = min(dist, mlen - copied);
       lz4_copy_back<DST_GLOBAL>(dst, op + copied, dist, chunk);
       copied += chunk;
+      if (dist < 2048u && dist < mlen) dist <<= 1;            // bytes [op-offset, op+copied) are periodic: 2*dist <= offset+copied
       if (DST_GLOBAL) __threadfence_block();
       __syncwarp();
       }
@@ -572,11 +607,15 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
         {
         uint32_t w[4] = {0, 0, 0, 0};
         if (WB == 4)
-          {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int p = 0; p < 4; ++p) w[e] |= (uint32_t)planes[p * pstride + i * 4 + e] << (8 * p);
+          { // 4x4 byte transpose: one word of each plane -> four elements
+          const uint32_t p0 = reinterpret_cast<const uint32_t*>(planes)[i];
+          const uint32_t p1 = reinterpret_cast<const uint32_t*>(planes + pstride)[i];
+          const uint32_t p2 = reinterpret_cast<const uint32_t*>(planes + 2 * pstride)[i];
+          const uint32_t p3 = reinterpret_cast<const uint32_t*>(planes + 3 * pstride)[i];
+          const uint32_t a01l = __byte_perm(p0, p1, 0x5140), a01h = __byte_perm(p0, p1, 0x7362);   // (p0.b0 p1.b0 p0.b1 p1.b1), (b2.. b3..)
+          const uint32_t a23l = __byte_perm(p2, p3, 0x5140), a23h = __byte_perm(p2, p3, 0x7362);
+          w[0] = __byte_perm(a01l, a23l, 0x5410); w[1] = __byte_perm(a01l, a23l, 0x7632);
+          w[2] = __byte_perm(a01h, a23h, 0x5410); w[3] = __byte_perm(a01h, a23h, 0x7632);
           }
         else if (WB == 2)
           {
