@@ -217,7 +217,19 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL may print a version banner on stdout while it initialises; stdout must carry exactly one
+        # JSON line, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     devname = torch.cuda.get_device_name(local)
 
     W, H = (FULL_W, FULL_H)
