@@ -114,6 +114,22 @@ TB200_API void tb200_event_destroy(void* ev);
 TB200_API int tb200_event_record(tb200_ctx* ctx, void* ev);
 TB200_API float tb200_event_elapsed_ms(void* start, void* stop);   /* synchronises on `stop` */
 
+/* extra streams / events (the archive layer overlaps H2D, kernels and D2H with them) */
+TB200_API void* tb200_stream_create(void);
+TB200_API void tb200_stream_destroy(void* stream);
+TB200_API int tb200_memcpy_h2d_on(void* stream, void* d, const void* h, uint64_t bytes);
+TB200_API int tb200_memcpy_d2h_on(void* stream, void* h, const void* d, uint64_t bytes);
+TB200_API int tb200_event_record_on(void* stream, void* ev);
+TB200_API int tb200_stream_wait_event(void* stream, void* ev);
+TB200_API int tb200_event_sync(void* ev);
+TB200_API int tb200_stream_sync(void* stream);
+TB200_API void* tb200_event_create_notiming(void);
+TB200_API int tb200_pointer_is_pinned_host(const void* p);
+
+/* exponents of the chunked FPC writer (hash_info byte 0x12): 4-entry FCM, 16-entry DFCM tables */
+#define TB200_V1_E1 2
+#define TB200_V1_E2 4
+
 #ifdef __cplusplus
 }
 #endif
