@@ -79,6 +79,10 @@ TB200_API int tb200_lz4_encode(tb200_ctx* ctx, int wordsize, const void* d_in, u
 /* inverse: LZ4_decompress_safe (lz4/lz4.c:2078) + trico_transpose_uint*_soa_to_aos */
 TB200_API int tb200_lz4_decode(tb200_ctx* ctx, int wordsize, const uint8_t* d_sizes, const uint8_t* d_payload,
                      uint64_t payload_bytes, uint64_t n, int log2_chunk, void* d_out);
+/* same without the stream synchronisation: malformed blocks set *d_status (a device word the caller
+ * zeroed) to 1; the caller reads it after its own synchronisation */
+TB200_API int tb200_lz4_decode_async(tb200_ctx* ctx, int wordsize, const uint8_t* d_sizes, const uint8_t* d_payload,
+                     uint64_t payload_bytes, uint64_t n, int log2_chunk, void* d_out, uint32_t* d_status);
 /* reference-format (v0) planes: `nplanes` whole-plane LZ4 blocks at d_base + offsets[p] of
  * nbytes[p] compressed bytes, each decoding to n bytes; merged into n elements of nplanes bytes. */
 TB200_API int tb200_lz4_decode_v0(tb200_ctx* ctx, int nplanes, const uint8_t* d_base, const uint64_t* offsets,
@@ -105,6 +109,7 @@ TB200_API void* tb200_host_alloc_pinned(uint64_t bytes);
 TB200_API void tb200_host_free_pinned(void* h);
 TB200_API int tb200_memcpy_h2d(tb200_ctx* ctx, void* d, const void* h, uint64_t bytes);   /* async on ctx stream */
 TB200_API int tb200_memcpy_d2h(tb200_ctx* ctx, void* h, const void* d, uint64_t bytes);   /* async on ctx stream */
+TB200_API int tb200_memset_d(tb200_ctx* ctx, void* d, int value, uint64_t bytes);         /* async on ctx stream */
 TB200_API int tb200_device_count(void);
 /* 1 if p points to device (or managed) memory, 0 for ordinary / pinned host memory */
 TB200_API int tb200_pointer_is_device(const void* p);

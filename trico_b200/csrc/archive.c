@@ -29,13 +29,21 @@ const char* trico_b200_last_error(void) { return g_err; }
  * Workers: a context (device + stream + kernel workspace) with two growable device buffers.
  * Archives borrow one for their lifetime; raw codec / transpose calls borrow one per call.
  * ------------------------------------------------------------------------------------------ */
+#define PIPE_NBUF 3                      /* ring depth of the slab pipeline */
 typedef struct
   {
   tb200_ctx* ctx;
   uint8_t* d_raw;  uint64_t raw_cap;     /* uncompressed elements */
   uint8_t* d_enc;  uint64_t enc_cap;     /* encoded stream bytes */
-  uint64_t* d_scalar;                    /* 64 bytes of device scalars */
+  uint64_t* d_scalar;                    /* 64 bytes of device scalars: [0] stream bytes, [1..3] slab totals, [7] status */
   int busy;
+  /* slab pipeline (host <-> device copies overlapped with the kernels, see write_stream_pipelined) */
+  int pipe_ready;
+  void* s_h2d; void* s_d2h;
+  void* ev_h2d[PIPE_NBUF]; void* ev_k[PIPE_NBUF]; void* ev_d2h[PIPE_NBUF];
+  uint8_t* d_ring; uint64_t ring_cap;    /* 2 * PIPE_NBUF slots of ring_cap / (2 * PIPE_NBUF) bytes */
+  uint8_t* d_table; uint64_t table_cap;  /* u16 chunk sizes of the stream in flight */
+  uint64_t* h_scalar;                    /* page-locked, 64 bytes */
   } worker;
 
 #define MAX_WORKERS 64
@@ -273,6 +281,256 @@ static int need_worker(archive* a)
   }
 
 /* ------------------------------------------------------------------------------------------
+ * Slab pipeline.  A host-resident stream larger than a few slabs is cut into chunk-aligned slabs;
+ * slab i+1 crosses PCIe while slab i is in the kernels and slab i-1 travels back, on three CUDA
+ * streams chained by events.  Chunks are independent, so the bytes are identical to the one-shot
+ * path: only the schedule differs.  (The reference has no counterpart: it is one CPU thread.)
+ * ------------------------------------------------------------------------------------------ */
+static uint64_t slab_bytes(void)
+  {
+  const char* s = getenv("TRICO_B200_SLAB_MB");
+  long mb = s ? atol(s) : 0;
+  if (mb < 1 || mb > 1024) mb = 32;
+  return (uint64_t)mb << 20;
+  }
+
+static int pipe_init(worker* w)
+  {
+  if (w->pipe_ready) return 1;
+  w->s_h2d = tb200_stream_create();
+  w->s_d2h = tb200_stream_create();
+  w->h_scalar = (uint64_t*)tb200_host_alloc_pinned(64);
+  int ok = w->s_h2d && w->s_d2h && w->h_scalar;
+  for (int i = 0; i < PIPE_NBUF; ++i)
+    {
+    w->ev_h2d[i] = tb200_event_create_notiming();
+    w->ev_k[i] = tb200_event_create_notiming();
+    w->ev_d2h[i] = tb200_event_create_notiming();
+    ok = ok && w->ev_h2d[i] && w->ev_k[i] && w->ev_d2h[i];
+    }
+  if (!ok) { set_dev_err(); return 0; }
+  w->pipe_ready = 1;
+  return 1;
+  }
+
+/* waits until nothing of the pipeline is in flight (also the error path: buffers are reused) */
+static int pipe_drain(worker* w)
+  {
+  int ok = tb200_stream_sync(w->s_h2d);
+  ok = tb200_ctx_sync(w->ctx) && ok;
+  ok = tb200_stream_sync(w->s_d2h) && ok;
+  return ok;
+  }
+
+static int pipe_buffers(worker* w, uint64_t slot_bytes, uint64_t table_bytes)
+  {
+  const uint64_t need = slot_bytes * 2 * PIPE_NBUF;
+  if (need > w->ring_cap)
+    {
+    if (!pipe_drain(w)) { set_dev_err(); return 0; }
+    if (w->d_ring) tb200_device_free(w->d_ring);
+    w->d_ring = (uint8_t*)tb200_device_alloc(need);
+    w->ring_cap = w->d_ring ? need : 0;
+    if (!w->d_ring) { set_dev_err(); return 0; }
+    }
+  if (!ensure(&w->d_table, &w->table_cap, table_bytes + 64, w)) return 0;
+  return 1;
+  }
+
+typedef struct
+  {
+  int codec, ws, nc, log2c;
+  uint64_t n;               /* scalars per component (FPC) / elements (LZ4) */
+  uint64_t unit;            /* scalars (elements) per chunk range */
+  uint64_t slab_ranges;     /* ranges per slab */
+  uint64_t nranges, nslabs;
+  uint64_t range_raw;       /* raw bytes of one full range (all components / the whole element) */
+  uint32_t nsub;            /* chunks per range */
+  uint64_t chunk_bound;     /* worst-case bytes of one chunk */
+  } slab_plan;
+
+static int plan_slabs(slab_plan* p, int type, uint32_t count, int log2c)
+  {
+  int ws = 0, nc = 0, pc = 0;
+  p->codec = tb200_stream_layout(type, &ws, &nc, &pc);
+  if (!p->codec) return 0;
+  p->ws = ws; p->nc = nc; p->log2c = log2c;
+  p->n = (uint64_t)count * pc;
+  p->unit = (uint64_t)1 << log2c;
+  p->nranges = (p->n + p->unit - 1) >> log2c;
+  p->nsub = (uint32_t)(p->codec == 1 ? nc : ws);
+  p->range_raw = p->unit * (uint64_t)ws * (p->codec == 1 ? nc : 1);
+  uint64_t r = slab_bytes() / p->range_raw;
+  /* whole encode / decode tiles (12 resp. up to 128 ranges): 384 = lcm */
+  if (p->codec == 1) r = r / 384 * 384;
+  if (r < 384 && p->codec == 1) r = 384;
+  if (r < 1) r = 1;
+  p->slab_ranges = r;
+  p->nslabs = (p->nranges + r - 1) / r;
+  /* worst-case bytes of one chunk, recovered from the public whole-stream bound of one range */
+  const uint32_t one_range_count = (uint32_t)((p->unit + pc - 1) / pc);
+  const uint64_t b1 = tb200_v1_stream_bound(type, one_range_count, log2c);
+  const uint64_t nchb = tb200_v1_nchunks(type, one_range_count, log2c);
+  p->chunk_bound = (b1 - TB200_V1_FIXED_BYTES - 64 - 2 * nchb) / (nchb ? nchb : 1);
+  return 1;
+  }
+
+static int use_pipeline(const slab_plan* p, uint64_t raw_bytes)
+  {
+  const char* s = getenv("TRICO_B200_NO_PIPELINE");
+  if (s && s[0] == '1') return 0;
+  return p->nslabs >= 3 && raw_bytes >= (8u << 20);
+  }
+
+static int write_stream_pipelined(archive* a, int type, const uint8_t* data, uint32_t count, const slab_plan* p)
+  {
+  worker* w = a->w;
+  if (!pipe_init(w)) return 0;
+  const uint64_t nch = p->nranges * p->nsub;
+  const uint64_t slab_raw = p->slab_ranges * p->range_raw;
+  const uint64_t slab_enc = p->slab_ranges * p->nsub * p->chunk_bound + 256;
+  const uint64_t slot = ((slab_raw > slab_enc ? slab_raw : slab_enc) + 4096 + 255) & ~(uint64_t)255;
+  if (!pipe_buffers(w, slot, 2 * nch)) return 0;
+  /* nothing of an earlier call may still be using the ring or the scalars */
+  if (!pipe_drain(w)) { set_dev_err(); return 0; }
+  const uint64_t head = TB200_V1_FIXED_BYTES + 2 * nch;
+  if (!buffer_reserve(a, head)) return 0;
+  const uint64_t stream_off = a->size;
+  uint64_t pay = 0;                                    /* payload bytes placed so far */
+  void* cs = tb200_ctx_stream(w->ctx);
+  int ok = 1;
+  const int info = p->codec == 1 ? (((TB200_V1_E1 >> 1) << 4) | (TB200_V1_E2 >> 1)) : 0;
+
+  for (uint64_t s = 0; ok && s <= p->nslabs; ++s)
+    {
+    if (s < p->nslabs)
+      {
+      const int k = (int)(s % PIPE_NBUF);
+      const uint64_t r0 = s * p->slab_ranges;
+      uint64_t r1 = r0 + p->slab_ranges; if (r1 > p->nranges) r1 = p->nranges;
+      const uint64_t e0 = r0 << p->log2c;
+      uint64_t e1 = r1 << p->log2c; if (e1 > p->n) e1 = p->n;
+      const uint64_t esz = (uint64_t)p->ws * (p->codec == 1 ? p->nc : 1);
+      uint8_t* d_in = w->d_ring + (uint64_t)k * slot;
+      uint8_t* d_out = w->d_ring + (uint64_t)(PIPE_NBUF + k) * slot;
+      if (s >= PIPE_NBUF) ok = ok && tb200_stream_wait_event(w->s_h2d, w->ev_k[k]);
+      ok = ok && tb200_memcpy_h2d_on(w->s_h2d, d_in, data + e0 * esz, (e1 - e0) * esz);
+      ok = ok && tb200_event_record_on(w->s_h2d, w->ev_h2d[k]);
+      ok = ok && tb200_stream_wait_event(cs, w->ev_h2d[k]);
+      if (s >= PIPE_NBUF) ok = ok && tb200_stream_wait_event(cs, w->ev_d2h[k]);
+      uint8_t* d_sizes = w->d_table + 2 * r0 * p->nsub;
+      if (p->codec == 1)
+        ok = ok && tb200_fpc_encode(w->ctx, p->ws, p->nc, d_in, e1 - e0, p->log2c, TB200_V1_E1, TB200_V1_E2, d_sizes, d_out, NULL, w->d_scalar + 1 + k);
+      else
+        ok = ok && tb200_lz4_encode(w->ctx, p->ws, d_in, e1 - e0, p->log2c, d_sizes, d_out, NULL, w->d_scalar + 1 + k);
+      ok = ok && tb200_memcpy_d2h(w->ctx, w->h_scalar + 1 + k, w->d_scalar + 1 + k, 8);
+      ok = ok && tb200_event_record_on(cs, w->ev_k[k]);
+      if (!ok) set_dev_err();
+      }
+    if (ok && s >= 1)
+      { /* slab s-1 has been encoded: its size is known, send it home */
+      const int k = (int)((s - 1) % PIPE_NBUF);
+      ok = tb200_event_sync(w->ev_k[k]);
+      if (!ok) { set_dev_err(); break; }
+      const uint64_t tot = w->h_scalar[1 + k];
+      if (tot > slot) { set_err("encoder returned an impossible size"); ok = 0; break; }
+      if (stream_off + head + pay + tot > a->cap)
+        { /* growing moves the buffer: copies in flight must land first */
+        ok = tb200_stream_sync(w->s_d2h);
+        if (!ok) { set_dev_err(); break; }
+        a->size = stream_off + head + pay;
+        if (!buffer_reserve(a, tot)) { a->size = stream_off; ok = 0; break; }
+        a->size = stream_off;
+        }
+      ok = tb200_memcpy_d2h_on(w->s_d2h, a->buffer + stream_off + head + pay, w->d_ring + (uint64_t)(PIPE_NBUF + k) * slot, tot) &&
+           tb200_event_record_on(w->s_d2h, w->ev_d2h[k]);
+      if (!ok) set_dev_err();
+      pay += tot;
+      }
+    }
+  /* size table, then the fixed header from the host */
+  ok = ok && tb200_memcpy_d2h_on(w->s_d2h, a->buffer + stream_off + TB200_V1_FIXED_BYTES, w->d_table, 2 * nch);
+  if (!pipe_drain(w)) ok = 0;
+  if (!ok) { if (g_err[0] == 0) set_dev_err(); return 0; }
+  uint8_t* h = a->buffer + stream_off;
+  h[0] = (uint8_t)type; put32(h + 1, count); h[5] = (uint8_t)info; h[6] = (uint8_t)p->log2c;
+  put32(h + 7, (uint32_t)pay); put32(h + 11, (uint32_t)(pay >> 32));
+  a->size = stream_off + head + pay;
+  if (a->version == 0) { a->version = 1; put32(a->buffer + 4, 1); }
+  return 1;
+  }
+
+/* v1 stream at a->data + start (host memory) -> host_dst (host memory) */
+static int read_stream_pipelined(archive* a, uint64_t start, const uint8_t* head, void* host_dst, const slab_plan* p)
+  {
+  worker* w = a->w;
+  if (!pipe_init(w)) return 0;
+  const uint64_t nch = p->nranges * p->nsub;
+  const uint64_t total = get64(head + 7);
+  const int info = head[5];
+  const uint8_t* table = a->data + start + TB200_V1_FIXED_BYTES;
+  const uint8_t* payload = table + 2 * nch;
+  const uint64_t slab_raw = p->slab_ranges * p->range_raw;
+  const uint64_t slab_enc_max = p->slab_ranges * p->nsub * 65535ull;      /* what the u16 table can describe */
+  /* payload offset of every slab: a host walk over the u16 sizes */
+  uint64_t* poff = (uint64_t*)malloc((p->nslabs + 1) * sizeof(uint64_t));
+  if (!poff) return 0;
+  uint64_t acc = 0, worst = 0;
+  for (uint64_t s = 0; s < p->nslabs; ++s)
+    {
+    poff[s] = acc;
+    const uint64_t c0 = s * p->slab_ranges * p->nsub;
+    uint64_t c1 = c0 + p->slab_ranges * p->nsub; if (c1 > nch) c1 = nch;
+    const uint8_t* t = table + 2 * c0;
+    uint64_t sum = 0;
+    for (uint64_t c = 0; c < c1 - c0; ++c) sum += (uint64_t)t[2 * c] | ((uint64_t)t[2 * c + 1] << 8);
+    acc += sum;
+    if (sum > worst) worst = sum;
+    }
+  poff[p->nslabs] = acc;
+  if (acc != total || worst > slab_enc_max) { free(poff); set_err("chunk size table disagrees with the stream header"); return 0; }
+  const uint64_t slot = ((slab_raw > worst ? slab_raw : worst) + 4096 + 255) & ~(uint64_t)255;
+  if (!pipe_buffers(w, slot, 2 * nch) || !pipe_drain(w)) { free(poff); return 0; }
+  void* cs = tb200_ctx_stream(w->ctx);
+  uint32_t* d_status = (uint32_t*)(w->d_scalar + 7);
+  int ok = tb200_memset_d(w->ctx, d_status, 0, 8);
+  ok = ok && tb200_memcpy_h2d(w->ctx, w->d_table, table, 2 * nch);
+  const uint64_t esz = (uint64_t)p->ws * (p->codec == 1 ? p->nc : 1);
+  for (uint64_t s = 0; ok && s < p->nslabs; ++s)
+    {
+    const int k = (int)(s % PIPE_NBUF);
+    const uint64_t r0 = s * p->slab_ranges;
+    uint64_t r1 = r0 + p->slab_ranges; if (r1 > p->nranges) r1 = p->nranges;
+    const uint64_t e0 = r0 << p->log2c;
+    uint64_t e1 = r1 << p->log2c; if (e1 > p->n) e1 = p->n;
+    const uint64_t plen = poff[s + 1] - poff[s];
+    /* keep the payload's alignment modulo 16 and leave room in front: the kernels read whole words */
+    uint8_t* d_in = w->d_ring + (uint64_t)k * slot + 64 + ((uintptr_t)(payload + poff[s]) & 15u);
+    uint8_t* d_out = w->d_ring + (uint64_t)(PIPE_NBUF + k) * slot;
+    if (s >= PIPE_NBUF) ok = ok && tb200_stream_wait_event(w->s_h2d, w->ev_k[k]);
+    ok = ok && tb200_memcpy_h2d_on(w->s_h2d, d_in, payload + poff[s], plen);
+    ok = ok && tb200_event_record_on(w->s_h2d, w->ev_h2d[k]);
+    ok = ok && tb200_stream_wait_event(cs, w->ev_h2d[k]);
+    if (s >= PIPE_NBUF) ok = ok && tb200_stream_wait_event(cs, w->ev_d2h[k]);
+    const uint8_t* d_sizes = w->d_table + 2 * r0 * p->nsub;
+    if (p->codec == 1)
+      ok = ok && tb200_fpc_decode(w->ctx, p->ws, p->nc, d_sizes, d_in, plen, e1 - e0, p->log2c, (info >> 4) << 1, (info & 15) << 1, d_out);
+    else
+      ok = ok && tb200_lz4_decode_async(w->ctx, p->ws, d_sizes, d_in, plen, e1 - e0, p->log2c, d_out, d_status);
+    ok = ok && tb200_event_record_on(cs, w->ev_k[k]);
+    ok = ok && tb200_stream_wait_event(w->s_d2h, w->ev_k[k]);
+    ok = ok && tb200_memcpy_d2h_on(w->s_d2h, (uint8_t*)host_dst + e0 * esz, d_out, (e1 - e0) * esz);
+    ok = ok && tb200_event_record_on(w->s_d2h, w->ev_d2h[k]);
+    }
+  free(poff);
+  if (!ok) set_dev_err();
+  ok = ok && tb200_memcpy_d2h(w->ctx, w->h_scalar + 7, d_status, 8);
+  if (!pipe_drain(w)) { if (ok) set_dev_err(); ok = 0; }
+  if (ok && (uint32_t)w->h_scalar[7] != 0) { set_err("malformed LZ4 block"); ok = 0; }
+  return ok;
+  }
+
+/* ------------------------------------------------------------------------------------------
  * writer: one routine for all stream types (trico.c:215-858).  `count` is the value stored in
  * the stream header.
  * ------------------------------------------------------------------------------------------ */
@@ -293,7 +551,14 @@ static int write_stream(void* h, int type, const void* data, uint32_t count)
   const uint64_t raw_bytes = nscalars * ws;
   const uint64_t bound = tb200_v1_stream_bound(type, count, log2c);
   const void* d_in = data;
-  if (raw_bytes && !tb200_pointer_is_device(data))
+  const int data_on_device = raw_bytes ? tb200_pointer_is_device(data) : 0;
+  if (raw_bytes && !data_on_device)
+    {
+    slab_plan plan;
+    if (plan_slabs(&plan, type, count, log2c) && use_pipeline(&plan, raw_bytes))
+      return write_stream_pipelined(a, type, (const uint8_t*)data, count, &plan);
+    }
+  if (raw_bytes && !data_on_device)
     {
     if (!ensure(&w->d_raw, &w->raw_cap, raw_bytes + 64, w)) return 0;
     if (!tb200_memcpy_h2d(w->ctx, w->d_raw, data, raw_bytes)) { set_dev_err(); return 0; }
@@ -434,6 +699,16 @@ static int read_stream(void* h, int type, void** out, int alloc_result)
       }
     else host_dst = *out;
     const int dst_on_device = !alloc_result && tb200_pointer_is_device(host_dst);
+    slab_plan plan;
+    if (a->version == 1 && !dst_on_device && !a->data_on_device && head[6] >= 5 && head[6] <= 15 &&
+        plan_slabs(&plan, type, count, head[6]) && use_pipeline(&plan, raw_bytes))
+      {
+      if (!read_stream_pipelined(a, start, head, host_dst, &plan)) { if (alloc_result) free(host_dst); return 0; }
+      if (alloc_result) *out = host_dst;
+      a->pos = end;
+      peek_next_type(a);
+      return 1;
+      }
     if (dst_on_device) d_dst = host_dst;
     else
       {

@@ -457,22 +457,24 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
     }
   }
 
-// Assembly: chunk g's block sits at scratch + g*slot with its size in sizes[g]; tiles of 64
-// chunks take their base from a look-back over tile totals (all known up front, so no waiting).
-constexpr int LZ4_ASM_THREADS = 64;
+// Assembly: chunk g's block sits at scratch + g*slot with its size in sizes[g]; tiles of
+// LZ4_ASM_TILE chunks take their base from a look-back over tile totals (all known up front, so
+// no waiting), then the CTA's 8 warps copy the tile's blocks to their final offsets.
+constexpr int LZ4_ASM_THREADS = 256;
+constexpr int LZ4_ASM_TILE = 128;
 
 __global__ void __launch_bounds__(LZ4_ASM_THREADS)
 lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
   {
-  __shared__ uint32_t sh_off[LZ4_ASM_THREADS];
-  __shared__ uint32_t sh_sz[LZ4_ASM_THREADS];
-  __shared__ uint32_t sh_wsum[LZ4_ASM_THREADS / 32];
+  __shared__ uint32_t sh_off[LZ4_ASM_TILE];
+  __shared__ uint32_t sh_sz[LZ4_ASM_TILE];
+  __shared__ uint32_t sh_wsum[LZ4_ASM_TILE / 32];
   __shared__ uint64_t sh_base;
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t tile = blockIdx.x;
-  const uint64_t g0 = (uint64_t)tile * LZ4_ASM_THREADS;
+  const uint64_t g0 = (uint64_t)tile * LZ4_ASM_TILE;
   uint32_t mysz = 0;
-  if (g0 + threadIdx.x < nchunks)
+  if (threadIdx.x < LZ4_ASM_TILE && g0 + threadIdx.x < nchunks)
     {
     const uint8_t* sz = a.sizes + 2 * (g0 + threadIdx.x);
     mysz = (uint32_t)sz[0] | ((uint32_t)sz[1] << 8);
@@ -484,13 +486,16 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
     const uint32_t up = __shfl_up_sync(FULL, incl, o);
     if (lane >= (unsigned)o) incl += up;
     }
-  if (lane == 31) sh_wsum[warp] = incl;
+  if (lane == 31 && warp < LZ4_ASM_TILE / 32) sh_wsum[warp] = incl;
   __syncthreads();
   uint32_t wbase = 0, tsum = 0;
 #pragma unroll
-  for (int w = 0; w < LZ4_ASM_THREADS / 32; ++w) { const uint32_t t = sh_wsum[w]; if (w < (int)warp) wbase += t; tsum += t; }
-  sh_off[threadIdx.x] = wbase + incl - mysz;
-  sh_sz[threadIdx.x] = mysz;
+  for (int w = 0; w < LZ4_ASM_TILE / 32; ++w) { const uint32_t t = sh_wsum[w]; if (w < (int)warp) wbase += t; tsum += t; }
+  if (threadIdx.x < LZ4_ASM_TILE)
+    {
+    sh_off[threadIdx.x] = wbase + incl - mysz;
+    sh_sz[threadIdx.x] = mysz;
+    }
   if (warp == 0)
     {
     const uint64_t excl = lookback_exclusive(a.desc, tile, tsum);
@@ -501,7 +506,7 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
       }
     }
   __syncthreads();
-  for (uint32_t c = warp; c < LZ4_ASM_THREADS && g0 + c < nchunks; c += LZ4_ASM_THREADS / 32)
+  for (uint32_t c = warp; c < LZ4_ASM_TILE && g0 + c < nchunks; c += LZ4_ASM_THREADS / 32)
     {
     const uint32_t nbytes = sh_sz[c];
     const uint8_t* src = a.scratch + (g0 + c) * a.slot;                  // 16-byte aligned
@@ -510,18 +515,57 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
     if (head > nbytes) head = nbytes;
     if (lane < head) dst[lane] = src[lane];
     const uint32_t nvec = (nbytes - head) >> 4;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(src + (head & ~3u));
-    const unsigned sh = (head & 3u) * 8u;
     uint4* dv = reinterpret_cast<uint4*>(dst + head);
-#pragma unroll 4
-    for (uint32_t i = lane; i < nvec; i += 32)
+    if ((head & 3u) == 0)
+      { // source words line up with the destination vectors
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(src + head);
+      const unsigned sh = 0; (void)sh;
+      constexpr int UN = 4;
+      for (uint32_t i0 = 0; i0 < nvec; i0 += 32 * UN)
+        {
+        uint32_t w[UN][4];
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+          {
+          const uint32_t i = i0 + lane + 32 * u;
+          if (i < nvec) { const uint32_t* q = sw + 4 * i; w[u][0] = __ldcs(q); w[u][1] = __ldcs(q + 1); w[u][2] = __ldcs(q + 2); w[u][3] = __ldcs(q + 3); }
+          }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+          {
+          const uint32_t i = i0 + lane + 32 * u;
+          if (i < nvec) dv[i] = make_uint4(w[u][0], w[u][1], w[u][2], w[u][3]);
+          }
+        }
+      }
+    else
       {
-      const uint32_t* s = sw + 4 * i;
-      const uint32_t w0 = s[0], w1 = s[1], w2 = s[2], w3 = s[3], w4 = s[4];
-      uint4 o;
-      o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
-      o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
-      dv[i] = o;
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(src + (head & ~3u));
+      const unsigned sh = (head & 3u) * 8u;
+      constexpr int UN = 4;
+      for (uint32_t i0 = 0; i0 < nvec; i0 += 32 * UN)
+        {
+        uint32_t w[UN][5];
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+          {
+          const uint32_t i = i0 + lane + 32 * u;
+          if (i < nvec)
+            {
+            const uint32_t* q = sw + 4 * i;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) w[u][j] = __ldcs(q + j);
+            }
+          }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+          {
+          const uint32_t i = i0 + lane + 32 * u;
+          if (i < nvec)
+            dv[i] = make_uint4(__funnelshift_r(w[u][0], w[u][1], sh), __funnelshift_r(w[u][1], w[u][2], sh),
+                               __funnelshift_r(w[u][2], w[u][3], sh), __funnelshift_r(w[u][3], w[u][4], sh));
+          }
+        }
       }
     const uint32_t done = head + (nvec << 4);
     if (done + lane < nbytes) dst[done + lane] = src[done + lane];
