@@ -158,6 +158,58 @@ def test_lz4_decode_of_oracle_streams(dev, oracle):
             assert dev.decode_stream(s).tobytes() == data.tobytes(), (ty, log2c)
 
 
+def _lz_varied_bytes(seed, n):
+    """bytes with periodic runs of many periods (1..40 and a few long ones) and lengths, separated by
+    random literal stretches: exercises every copy path of the block decoder"""
+    rng = np.random.default_rng(seed)
+    out = []
+    total = 0
+    periods = list(range(1, 41)) + [48, 64, 100, 255, 256, 1000, 5000]
+    while total < n:
+        lit = int(rng.choice([0, 1, 3, 14, 15, 16, 40, 270, 600]))
+        out.append(rng.integers(0, 256, lit, dtype=np.uint8))
+        per = int(rng.choice(periods))
+        length = int(rng.choice([4, 5, 18, 19, 20, 33, 64, 65, 100, 300, 700, 3000, 9000]))
+        pat = rng.integers(0, 256, per, dtype=np.uint8)
+        out.append(np.resize(pat, per + length))
+        total += lit + per + length
+    return np.concatenate(out)[:n]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_lz4_decode_varied_sequences(dev, oracle, seed):
+    """blocks written by the CPU oracle's compressor and by the GPU compressor, with short and long
+    periods, short and long literal runs: GPU decode must reproduce the bytes exactly"""
+    data = _lz_varied_bytes(seed, 200000 + 777 * seed)
+    for ty, arr in ((17, data), (18, data[:data.size // 2 * 2].view(np.uint16)), (19, data[:data.size // 4 * 4].view(np.uint32)),
+                    (20, data[:data.size // 8 * 8].view(np.uint64))):
+        for log2c in (8, 11, 14):
+            s = oracle.v1_write_stream(ty, arr, arr.size, log2c)
+            assert dev.decode_stream(s).tobytes() == arr.tobytes(), (ty, log2c, "oracle-written")
+            g = dev.encode_stream(ty, arr, arr.size, log2c)
+            _, _, back, _ = oracle.v1_read_stream(b"Trco\x01\0\0\0" + g, 8)
+            assert back.tobytes() == arr.tobytes(), (ty, log2c, "gpu-written, oracle-read")
+            assert dev.decode_stream(g).tobytes() == arr.tobytes(), (ty, log2c, "gpu-written")
+
+
+def test_lz4_decode_rejects_malformed_blocks(dev, oracle):
+    """corrupted payload bytes must produce an error or garbage, never a crash; an intact stream still decodes after"""
+    from trico_b200 import TB200Error
+    data = _lz_varied_bytes(5, 60000)
+    s = bytearray(oracle.v1_write_stream(17, data, data.size, 12))
+    rng = np.random.default_rng(9)
+    nch = (data.size + 4095) // 4096
+    for _ in range(20):
+        t = bytearray(s)
+        for _ in range(8):
+            t[15 + 2 * nch + int(rng.integers(0, len(s) - 15 - 2 * nch))] = int(rng.integers(0, 256))
+        try:
+            dev.decode_stream(bytes(t))
+        except TB200Error:
+            pass
+    assert dev.decode_stream(bytes(s)).tobytes() == data.tobytes()
+
+
 def test_lz4_ratio_close_to_reference(dev, ref, oracle, golden):
     """same block size, GPU matcher vs the reference's LZ4_compress_default"""
     data, cnt = _stream_input(golden, 3)

@@ -231,8 +231,8 @@ static int launch_fpc_decode(tb200_ctx* c, FpcDecodeArgs a)
   constexpr int NWARPS = NCOMP * R;
   a.ntiles = (a.nranges + 32 * R - 1) / (32 * R);
   if (!ws_prepare(c, a.ntiles, &a.ticket, &a.desc)) return 0;
-  const size_t smem = (((size_t)NWARPS * 32 * WIN::WORDS * 4 + 15) & ~(size_t)15) +
-                      (size_t)32 * R * (SB * NCOMP + 1) * sizeof(W) +
+  const size_t smem = (size_t)NWARPS * 32 * WIN::VECS * 16 +
+                      (size_t)32 * R * (SB * NCOMP * (sizeof(W) / 4) + 4) * 4 +
                       (size_t)NWARPS * 32 * ((1u << a.e1) + (1u << a.e2)) * sizeof(W);
   if (!set_smem(fpc_decode_kernel<W, NCOMP, R, SB>, smem, c)) return 0;
   fpc_decode_kernel<W, NCOMP, R, SB><<<a.ntiles, NWARPS * 32, smem, c->stream>>>(a);

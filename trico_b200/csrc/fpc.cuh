@@ -388,10 +388,11 @@ struct FpcDecodeArgs
 template <typename W, int SB> struct FpcWindow
   {
   using TR = FpcTraits<W>;
-  // bytes one sub-block can consume + 3 bytes of misalignment, in 32-bit words, made odd
-  static constexpr int BYTES = (SB / TR::GROUP) * TR::HDR + SB * TR::WBYTES + 3;
-  static constexpr int WORDS0 = (BYTES + 3) / 4 + 1;      // +1: the unaligned fetch reads one word further
-  static constexpr int WORDS = WORDS0 | 1;
+  // A lane's window starts at the 16-byte boundary at or below its read position and must hold
+  // everything one sub-block can consume (code words + SB full residuals) plus the words the
+  // unaligned big-endian fetch touches behind the last byte.
+  static constexpr int BYTES = 15 + (SB / TR::GROUP) * TR::HDR + SB * TR::WBYTES + (TR::WBYTES == 4 ? 8 : 12);
+  static constexpr int VECS = (BYTES + 15) / 16;
   };
 
 template <typename W, int NCOMP, int R, int SB>
@@ -402,12 +403,16 @@ fpc_decode_kernel(const FpcDecodeArgs a)
   using WIN = FpcWindow<W, SB>;
   constexpr int NWARPS = NCOMP * R;
   constexpr int NTHREADS = NWARPS * 32;
-  constexpr int ROW = SB * NCOMP + 1;                     // staging row stride (odd: conflict-free column writes)
+  constexpr int WV = WIN::VECS;                           // 16-byte vectors per lane window
+  constexpr int WPV = sizeof(W) / 4;                      // 32-bit words per value
+  constexpr int ROWV = SB * NCOMP * WPV / 4;              // 16-byte vectors per staged row
+  constexpr int ROWW = SB * NCOMP * WPV + 4;              // staging row stride in words (rows stay 16-byte aligned)
+  static_assert((SB * NCOMP * WPV) % 4 == 0, "staged rows must be whole vectors");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t nt1 = 1u << a.e1, nt2 = 1u << a.e2;
-  uint32_t* win = reinterpret_cast<uint32_t*>(smem_raw);                               // [NWARPS][32][WIN::WORDS]
-  W* stagebuf = reinterpret_cast<W*>(smem_raw + ((size_t)NWARPS * 32 * WIN::WORDS * 4 + 15 & ~(size_t)15)); // [32*R][ROW]
-  W* tables = stagebuf + (size_t)32 * R * ROW;                                         // [NWARPS][nt1+nt2][32]
+  uint32_t* win = reinterpret_cast<uint32_t*>(smem_raw);                               // [NWARPS][32][WV*4]
+  uint32_t* stagebuf = win + (size_t)NWARPS * 32 * WV * 4;                             // [32*R][ROWW]
+  W* tables = reinterpret_cast<W*>(stagebuf + (size_t)32 * R * ROWW);                  // [NWARPS][nt1+nt2][32]
   __shared__ uint32_t sh_tile;
   __shared__ uint32_t sh_scan[NTHREADS];
   __shared__ uint32_t sh_wsum[NWARPS];
@@ -453,16 +458,27 @@ fpc_decode_kernel(const FpcDecodeArgs a)
   const uint64_t k = (uint64_t)tile * (32 * R) + klocal;
   const uint32_t S = 1u << a.log2S;
   uint32_t cnt = 0;
-  uint64_t pos = 0;                                        // byte offset of the next unread byte in payload
+  // Byte positions are kept relative to tb16, the 16-byte boundary at or below the tile's first
+  // payload byte, so all per-lane arithmetic is 32-bit.  relA = position of the next unread byte.
+  const uint8_t* tb = a.payload + sh_base;
+  const uint32_t A = (uint32_t)reinterpret_cast<uintptr_t>(tb) & 15u;
+  const uint8_t* tb16 = tb - A;
+  uint32_t relA = A;
   if (k < a.nranges)
     {
     const uint64_t lo = k << a.log2S;
     cnt = (uint32_t)((a.n - lo < S) ? (a.n - lo) : S);
-    pos = sh_base + sh_scan[klocal * NCOMP + c];
+    relA = A + sh_scan[klocal * NCOMP + c];
     }
+  // first byte past the payload, relative to tb16 (window copies never read at or beyond it)
+  const uint64_t end64 = (uint64_t)(a.payload + a.payload_bytes - tb16);
+  const uint32_t endoff = a.payload_bytes <= sh_base ? 0u : (end64 > 0x7fffffffull ? 0x7fffffffu : (uint32_t)end64);
+  const uint32_t last16 = endoff ? ((endoff - 1u) & ~15u) : 0u;
   // number of sub-blocks = that of the fullest chunk in the CTA (range 0 of the tile is never shorter)
   const uint64_t lo0 = ((uint64_t)tile * (32 * R)) << a.log2S;
   const uint32_t cnt0 = (uint32_t)((a.n - lo0 < S) ? (a.n - lo0) : S);
+  // every range of the tile is complete (S values) unless the tile holds the stream's last range
+  const bool full_tile = ((uint64_t)tile + 1) * (32 * R) < a.nranges;
 
   W* T1 = tables + (size_t)warp * (nt1 + nt2) * 32 + lane;
   W* T2 = T1 + (size_t)nt1 * 32;
@@ -470,39 +486,42 @@ fpc_decode_kernel(const FpcDecodeArgs a)
   FpcLaneState<W> st; st.pred1 = 0; st.pred2 = 0; st.last = 0; st.c1 = 0; st.c2 = 0;
   const uint32_t m2 = nt2 - 1;
 
-  uint32_t* wrow = win + ((size_t)warp * 32 + lane) * WIN::WORDS;
-  uint32_t* wwarp = win + (size_t)warp * 32 * WIN::WORDS;
-  // start of the last 32-bit word that still holds a payload byte: window loads are clamped to it
-  const uint8_t* pay_last = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(a.payload) + (a.payload_bytes ? a.payload_bytes - 1 : 0)) & ~(uintptr_t)3);
-  W* srow = stagebuf + (size_t)klocal * ROW + c;
-  W* gout = reinterpret_cast<W*>(a.out);
+  const uint32_t* wrow = win + ((size_t)warp * 32 + lane) * WV * 4;
+  const uint32_t wwarp_s = (uint32_t)__cvta_generic_to_shared(win + (size_t)warp * 32 * WV * 4);
+  uint32_t* srow = stagebuf + (size_t)klocal * ROWW + c * WPV;
+  uint8_t* gout = reinterpret_cast<uint8_t*>(a.out);
+  const bool out_aligned = (reinterpret_cast<uintptr_t>(gout) & 15u) == 0;
 
-  for (uint32_t i0 = 0; i0 < cnt0; i0 += SB)
+  // Window refill: the warp's 32 windows are contiguous in shared memory ([lane][WV] vectors), so
+  // copy number ci lands at vector ci; its source is vector ci % WV of lane ci / WV's window.
+  // 16-byte cp.async copies (global -> shared without a register round trip), all in flight at once;
+  // bytes at or beyond the end of the payload are not read (src-size operand, zero filled).
+  auto fill = [&]()
     {
-    // a. refresh the windows of all 32 lanes of this warp: coalesced 4-byte cp.async copies
-    //    (global -> shared without a register round trip, all in flight at once)
-#pragma unroll 4
-    for (int l = 0; l < 32; ++l)
+    const uint32_t arel = relA & ~15u;
+#pragma unroll
+    for (int it = 0; it < WV; ++it)
       {
-      const uint64_t p = __shfl_sync(FULL, pos, l);
-      const uint8_t* base = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(a.payload) + p) & ~(uintptr_t)3);   // word-aligned address at or below the byte
-      for (int w = lane; w < WIN::WORDS; w += 32)
-        {
-        const uint8_t* q = base + 4 * w;
-        if (q > pay_last) q = pay_last;
-        const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(wwarp + l * WIN::WORDS + w);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(saddr), "l"(q) : "memory");
-        }
+      const uint32_t ci = (uint32_t)it * 32u + lane;
+      const uint32_t L = ci / (uint32_t)WV, v = ci - L * (uint32_t)WV;
+      const uint32_t off = __shfl_sync(FULL, arel, L) + 16u * v;
+      const int32_t rem = (int32_t)endoff - (int32_t)off;
+      const uint32_t ssz = rem >= 16 ? 16u : (rem > 0 ? (uint32_t)rem : 0u);
+      const uint32_t offc = off < last16 ? off : last16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(wwarp_s + 16u * ci), "l"(tb16 + offc), "r"(ssz) : "memory");
       }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    // pull the bytes this lane will want next time towards L2 while the copies land
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(a.payload + (pos + WIN::BYTES + 64 < a.payload_bytes ? pos + WIN::BYTES + 64 : pos)));
+    };
+
+  fill();
+  for (uint32_t i0 = 0; i0 < cnt0; i0 += SB)
+    {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 
-    // b. decode up to SB values of this lane's chunk
-    uint32_t bp = (uint32_t)(((uintptr_t)a.payload + pos) & 3);
-    const uint32_t bp0 = bp;
+    // b. decode up to SB values of this lane's chunk out of its window
+    const uint32_t bp0 = relA & 15u;
+    uint32_t bp = bp0;
     const uint32_t todo = (i0 < cnt) ? ((cnt - i0 < (uint32_t)SB) ? cnt - i0 : (uint32_t)SB) : 0;
 #pragma unroll 1
     for (uint32_t g = 0; g < (uint32_t)SB / TR::GROUP; ++g)
@@ -541,25 +560,41 @@ fpc_decode_kernel(const FpcDecodeArgs a)
         if (idx < todo)
           {
           const W v = fpc_decode_value<W, 32>(st, x, use2, T1, T2, a.e1, a.e2, m2);
-          srow[(size_t)idx * NCOMP] = v;
+          *reinterpret_cast<W*>(srow + (size_t)idx * NCOMP * WPV) = v;
           }
         }
       }
-    pos += bp - bp0;
+    relA += bp - bp0;
+    // the next window crosses L2 -> shared memory while the slab is flushed
+    if (i0 + SB < cnt0) fill();
     __syncthreads();
 
     // c. flush the staged slab: row r = range (tile*32R + r), values [i0, i0+SB) x NCOMP, contiguous
-    for (uint32_t r = warp; r < 32u * R; r += NWARPS)
+    if (full_tile && out_aligned)
       {
-      const uint64_t kr = (uint64_t)tile * (32 * R) + r;
-      if (kr >= a.nranges) break;
-      const uint64_t lo = kr << a.log2S;
-      const uint32_t rc = (uint32_t)((a.n - lo < S) ? (a.n - lo) : S);
-      if (i0 >= rc) continue;
-      const uint32_t nv = ((rc - i0 < (uint32_t)SB) ? rc - i0 : (uint32_t)SB) * NCOMP;
-      const W* sr = stagebuf + (size_t)r * ROW;
-      W* go = gout + (lo + i0) * NCOMP;
-      for (uint32_t q = lane; q < nv; q += 32) go[q] = sr[q];
+      uint8_t* tile_out = gout + ((((uint64_t)tile * (32 * R)) << a.log2S) + i0) * (NCOMP * sizeof(W));
+      const uint32_t row_bytes = (uint32_t)(NCOMP * sizeof(W)) << a.log2S;
+      for (uint32_t ci = threadIdx.x; ci < 32u * R * ROWV; ci += NTHREADS)
+        {
+        const uint32_t r = ci / (uint32_t)ROWV, v = ci - r * (uint32_t)ROWV;
+        const uint4 val = *reinterpret_cast<const uint4*>(stagebuf + (size_t)r * ROWW + 4u * v);
+        __stcs(reinterpret_cast<uint4*>(tile_out + (size_t)r * row_bytes + 16u * v), val);
+        }
+      }
+    else
+      {
+      for (uint32_t r = warp; r < 32u * R; r += NWARPS)
+        {
+        const uint64_t kr = (uint64_t)tile * (32 * R) + r;
+        if (kr >= a.nranges) break;
+        const uint64_t lo = kr << a.log2S;
+        const uint32_t rc = (uint32_t)((a.n - lo < S) ? (a.n - lo) : S);
+        if (i0 >= rc) continue;
+        const uint32_t nw = ((rc - i0 < (uint32_t)SB) ? rc - i0 : (uint32_t)SB) * NCOMP * WPV;
+        const uint32_t* sr = stagebuf + (size_t)r * ROWW;
+        uint32_t* go = reinterpret_cast<uint32_t*>(gout + (lo + i0) * (NCOMP * sizeof(W)));
+        for (uint32_t q = lane; q < nw; q += 32) go[q] = sr[q];
+        }
       }
     __syncthreads();
     }

@@ -573,9 +573,209 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
   }
 
 // ---------------------------------------------------------------------------------------------
+// In-place block decoder on shared memory (K6).  The compressed block sits at the END of the
+// plane's buffer, the output grows from the start: with LZ4's in-place margin
+// ((csize >> 8) + 32 bytes, lz4.h "LZ4_DECOMPRESS_INPLACE_MARGIN") the write position never
+// passes the read position, so one buffer serves both and every token / length byte is a
+// shared-memory read.  All copies are warp-wide: literals and far matches move 512 bytes per
+// step (16 per lane); near matches (offset <= 32: runs, interleaved index patterns) are periodic
+// and are generated from their first 64 bytes with independent 16-byte reads and stores.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t lz4_inplace_stride(uint32_t B)
+  { // output + in-place margin of the largest block + 32 bytes of slack for alignment and word read-ahead
+  return ((B + (lz4_block_bound(B) >> 8) + 32u + 48u) + 15u) & ~15u;
+  }
+
+// reads a length continuation (bytes of 255 terminated by a byte < 255, lz4.c:1629-1649) at ip;
+// 32 bytes are inspected per step.  Returns the sum and advances ip past the terminator.
+__device__ __forceinline__ uint32_t lz4_read_ext(const uint8_t* buf, uint32_t& ip, uint32_t iend)
+  {
+  const unsigned lane = lane_id();
+  uint32_t add = 0;
+  for (;;)
+    {
+    const uint32_t b = (ip + lane < iend) ? buf[ip + lane] : 0u;       // past the end: terminates, caller's bound checks fail
+    const unsigned m = __ballot_sync(FULL, b != 255u);
+    if (m == 0) { add += 255u * 32u; ip += 32; continue; }
+    const int e = __ffs((int)m) - 1;
+    add += 255u * (uint32_t)e + __shfl_sync(FULL, b, e);
+    ip += (uint32_t)e + 1u;
+    return add;
+    }
+  }
+
+// 16 bytes at an arbitrary shared-memory position (needs the word after the last byte readable)
+__device__ __forceinline__ uint4 smem_read128(const uint8_t* base, uint32_t pos)
+  {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (pos >> 2);
+  const unsigned sh = (pos & 3u) * 8u;
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+  }
+
+// Warp copy inside one shared-memory buffer, dst and src arbitrary.  FORWARD_OVERLAP: dst < src
+// and the regions may overlap (literals of the in-place decoder) - every batch is read completely
+// before it is written.  Otherwise the regions must not overlap at all (src + n <= dst).
+template <bool FORWARD_OVERLAP>
+__device__ __forceinline__ void lz4_smem_move(uint8_t* buf, uint32_t dst, uint32_t src, uint32_t n)
+  {
+  const unsigned lane = lane_id();
+  if (n <= 32)
+    {
+    uint32_t t = 0;
+    if (lane < n) t = buf[src + lane];
+    if (FORWARD_OVERLAP) __syncwarp();
+    if (lane < n) buf[dst + lane] = (uint8_t)t;
+    return;
+    }
+  uint32_t head = (16u - (dst & 15u)) & 15u;
+    {
+    uint32_t t = 0;
+    if (lane < head) t = buf[src + lane];
+    if (FORWARD_OVERLAP) __syncwarp();
+    if (lane < head) buf[dst + lane] = (uint8_t)t;
+    }
+  const uint32_t nv = (n - head) >> 4;
+  const uint32_t s0 = src + head, d0 = dst + head;
+  constexpr int UN = 4;
+  for (uint32_t i0 = 0; i0 < nv; i0 += 32 * UN)
+    {
+    uint4 v[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      {
+      const uint32_t i = i0 + lane + 32 * u;
+      if (i < nv) v[u] = smem_read128(buf, s0 + 16u * i);
+      }
+    if (FORWARD_OVERLAP) __syncwarp();
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      {
+      const uint32_t i = i0 + lane + 32 * u;
+      if (i < nv) *reinterpret_cast<uint4*>(buf + d0 + 16u * i) = v[u];
+      }
+    }
+  const uint32_t done = head + (nv << 4);
+    {
+    uint32_t t = 0;
+    if (done + lane < n) t = buf[src + done + lane];
+    if (FORWARD_OVERLAP) __syncwarp();
+    if (done + lane < n) buf[dst + done + lane] = (uint8_t)t;
+    }
+  }
+
+// Decodes the block buf[ip, iend) into buf[0, cap).  Returns the bytes produced or 0xffffffff.
+__device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip, uint32_t iend, uint32_t cap)
+  {
+  const unsigned lane = lane_id();
+  uint32_t op = 0;
+  if (ip >= iend) return 0xffffffffu;
+  for (;;)
+    {
+    if (ip >= iend) return 0xffffffffu;
+    // the token and the 31 bytes behind it in one read: short sequences need nothing else
+    const uint32_t b = (ip + lane < iend) ? buf[ip + lane] : 0u;
+    const uint32_t token = __shfl_sync(FULL, b, 0);
+    uint32_t lit = token >> 4;
+    uint32_t offset = 0;
+    bool have_offset = false;
+    if (lit < 15u)
+      { // literals (and, unless this is the last sequence, the offset) are already in registers
+      if (ip + 1u + lit > iend || op + lit > cap || op > ip + 1u) return 0xffffffffu;     // writes must stay behind the unread input
+      __syncwarp();
+      if (lane >= 1u && lane <= lit) buf[op + lane - 1u] = (uint8_t)b;
+      offset = __shfl_sync(FULL, b, (lit + 1u) & 31u) | (__shfl_sync(FULL, b, (lit + 2u) & 31u) << 8);
+      have_offset = true;
+      ip += 1u + lit; op += lit;
+      }
+    else
+      {
+      ip += 1;
+      if (lit == 15u) lit += lz4_read_ext(buf, ip, iend);
+      if (ip + lit > iend || op + lit > cap || op > ip) return 0xffffffffu;
+      lz4_smem_move<true>(buf, op, ip, lit);
+      ip += lit; op += lit;
+      }
+    if (ip >= iend) break;                          // last sequence has no match part
+    if (ip + 2u > iend) return 0xffffffffu;
+    if (!have_offset) offset = (uint32_t)buf[ip] | ((uint32_t)buf[ip + 1] << 8);
+    ip += 2;
+    uint32_t mlen = token & 15u;
+    if (mlen == 15u) mlen += lz4_read_ext(buf, ip, iend);
+    mlen += LZ4_MINMATCH;
+    // the match may not run over unread input (cannot happen for blocks that respect the margin)
+    if (offset == 0 || offset > op || op + mlen > cap || op + mlen > ip) return 0xffffffffu;
+    __syncwarp();                                   // literals of this sequence are visible
+    if (offset >= mlen)
+      lz4_smem_move<false>(buf, op, op - offset, mlen);
+    else if (offset > 32u)
+      { // periodic with a long period: grow by copying everything available, distance doubling
+      uint32_t copied = 0, dist = offset;
+      while (copied < mlen)
+        {
+        const uint32_t chunk = min(dist, mlen - copied);
+        lz4_smem_move<false>(buf, op + copied, op + copied - dist, chunk);
+        copied += chunk;
+        if (dist < 4096u) dist <<= 1;               // [op-offset, op+copied) is periodic: 2*dist <= offset + copied
+        __syncwarp();
+        }
+      }
+    else
+      { // Short period (runs, interleaved index patterns).  The first 64 output bytes are written
+        // byte-wise (lane l: bytes l and l+32 of the pattern); they then serve as a look-up table:
+        // the 16 bytes at any later position x are the 16 bytes at op + (x - op) mod offset, so the
+        // rest of the match is produced with independent 16-byte reads and stores, no further
+        // synchronisation and no dependence on the match length.
+      const uint8_t* ms = buf + op - offset;
+      // t mod offset by multiplication: inv = ceil(2^32 / offset) gives exact quotients for t < 2^16
+      // (offset 1 would need 2^32: there every index is 0 and inv = 0 with the mask below does that)
+      const uint32_t inv = offset == 1u ? 0u : 0xffffffffu / offset + 1u;
+      const uint32_t keep = offset == 1u ? 0u : 0xffffffffu;
+      auto modo = [&](uint32_t t) { return (t - offset * __umulhi(t, inv)) & keep; };
+      const uint32_t r0 = modo(lane), r1 = modo(lane + 32u);
+      const uint32_t q0 = ms[r0], q1 = ms[r1];
+      __syncwarp();
+      if (lane < mlen) buf[op + lane] = (uint8_t)q0;
+      if (lane + 32u < mlen) buf[op + lane + 32u] = (uint8_t)q1;
+      __syncwarp();
+      if (mlen > 64u)
+        {
+        const uint32_t from = op + 64u, end = op + mlen;
+        const uint32_t xa = (from + 15u) & ~15u;
+        if (xa >= end)
+          {
+          if (from + lane < end) { const uint32_t t = 64u + lane; buf[from + lane] = buf[op + modo(t)]; }
+          }
+        else
+          {
+          const uint32_t head = xa - from;
+          if (lane < head) { const uint32_t t = 64u + lane; buf[from + lane] = buf[op + modo(t)]; }
+          const uint32_t nv = (end - xa) >> 4;
+          const uint32_t t0 = xa - op;
+          for (uint32_t i = lane; i < nv; i += 32)
+            {
+            const uint32_t t = t0 + 16u * i;
+            const uint32_t sft = modo(t);
+            *reinterpret_cast<uint4*>(buf + xa + 16u * i) = smem_read128(buf, op + sft);
+            }
+          const uint32_t done = xa + (nv << 4);
+          if (done + lane < end) { const uint32_t t = done - op + lane; buf[done + lane] = buf[op + modo(t)]; }
+          }
+        }
+      }
+    op += mlen;
+    __syncwarp();
+    }
+  return op;
+  }
+
+// ---------------------------------------------------------------------------------------------
 // K6: per-block LZ4 decode fused with the plane merge (trico_transpose_uint*_soa_to_aos,
-// transpose_aos_to_soa.c:94-147).  CTA = WB warps, tile = one range; warp p decodes plane p
-// into shared memory, then the CTA writes the merged elements with 16-byte stores.
+// transpose_aos_to_soa.c:94-147).  CTA = WB warps, tile = one range of B elements:
+//   1. the whole CTA stages the tile's WB compressed blocks (contiguous in the payload) into the
+//      tails of the plane buffers with 16-byte cp.async copies, all in flight at once
+//   2. warp p decodes plane p in place (lz4_decode_inplace)
+//   3. the CTA writes the merged elements with 16-byte stores.
 // ---------------------------------------------------------------------------------------------
 struct Lz4DecodeArgs
   {
@@ -597,7 +797,7 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
   {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t B = 1u << a.log2B;
-  const uint32_t pstride = B + 16;
+  const uint32_t pstride = lz4_inplace_stride(B);
   uint8_t* planes = smem_raw;
   __shared__ uint32_t sh_tile;
   __shared__ uint64_t sh_base;
@@ -613,15 +813,14 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
     const uint64_t lo = (uint64_t)tile << a.log2B;
     const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
 
-    uint32_t off = 0, agg = 0, mine = 0;
+    uint32_t szs[WB];
+    uint32_t agg = 0;
 #pragma unroll
     for (int w = 0; w < WB; ++w)
       {
       const uint8_t* sz = a.sizes + 2 * ((uint64_t)tile * WB + w);
-      const uint32_t s = (uint32_t)sz[0] | ((uint32_t)sz[1] << 8);
-      if (w < (int)warp) off += s;
-      if (w == (int)warp) mine = s;
-      agg += s;
+      szs[w] = (uint32_t)sz[0] | ((uint32_t)sz[1] << 8);
+      agg += szs[w];
       }
     if (warp == 0)
       {
@@ -629,18 +828,63 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
       if (lane == 0) sh_base = excl;
       }
     __syncthreads();
-    const uint64_t start = sh_base + off;
+    const uint64_t base = sh_base;
+    const bool in_range = base + agg <= a.payload_bytes;
+
+    // 1. stage: block w goes to the tail of plane buffer w, at an offset congruent to its global
+    //    address modulo 16 so that the body moves as 16-byte cp.async copies
+    uint32_t my_ip = 0, my_end = 0;
+    bool sizes_ok = in_range;
+      {
+      uint64_t off = base;
+#pragma unroll
+      for (int w = 0; w < WB; ++w)
+        {
+        const uint32_t sz = szs[w];
+        if (sz > lz4_block_bound(B) || sz == 0) sizes_ok = false;
+        if (sizes_ok)
+          {
+          const uint8_t* src = a.payload + off;
+          const uint32_t al = (uint32_t)reinterpret_cast<uintptr_t>(src) & 15u;
+          const uint32_t d0 = ((pstride - 32u - sz - al) & ~15u) + al;           // block occupies [d0, d0 + sz)
+          uint8_t* dst = planes + (size_t)w * pstride + d0;
+          uint32_t head = (16u - al) & 15u; if (head > sz) head = sz;
+          const uint32_t nv = (sz - head) >> 4;
+          if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+          for (uint32_t i = threadIdx.x; i < nv; i += WB * 32)
+            {
+            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst + head + 16u * i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(src + head + 16u * i) : "memory");
+            }
+          const uint32_t done = head + (nv << 4);
+          if (done + threadIdx.x < sz) dst[done + threadIdx.x] = src[done + threadIdx.x];
+          if (w == (int)warp) { my_ip = d0; my_end = d0 + sz; }
+          }
+        off += sz;
+        }
+      }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // 2. decode in place
     uint32_t got = 0xffffffffu;
-    if (start + mine <= a.payload_bytes)
-      got = lz4_decompress_warp<false>(a.payload + start, mine, planes + (size_t)warp * pstride, cnt);
+    if (sizes_ok) got = lz4_decode_inplace(planes + (size_t)warp * pstride, my_ip, my_end, cnt);
     if (got != cnt && lane == 0) *a.status = 1;
     __syncthreads();
 
-    // merge: element i = bytes planes[p][i], p = 0..WB-1 (LSB first)
+    // 3. merge: element i = bytes planes[p][i], p = 0..WB-1 (LSB first)
     uint8_t* gout = reinterpret_cast<uint8_t*>(a.out) + lo * WB;
     if (WB == 1)
       {
-      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) gout[i] = planes[i];
+      if ((reinterpret_cast<uintptr_t>(gout) & 15u) == 0)
+        {
+        const uint32_t nvec = cnt >> 4;
+        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) reinterpret_cast<uint4*>(gout)[i] = reinterpret_cast<const uint4*>(planes)[i];
+        for (uint32_t i = (nvec << 4) + threadIdx.x; i < cnt; i += blockDim.x) gout[i] = planes[i];
+        }
+      else
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) gout[i] = planes[i];
       }
     else if ((reinterpret_cast<uintptr_t>(gout) & 15u) == 0)
       {
@@ -662,17 +906,21 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
           w[2] = __byte_perm(a01h, a23h, 0x5410); w[3] = __byte_perm(a01h, a23h, 0x7632);
           }
         else if (WB == 2)
-          {
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            w[e >> 1] |= ((uint32_t)planes[i * 8 + e] | ((uint32_t)planes[pstride + i * 8 + e] << 8)) << (16 * (e & 1));
+          { // eight elements: one 8-byte group of each plane
+          const uint2 q0 = reinterpret_cast<const uint2*>(planes)[i];
+          const uint2 q1 = reinterpret_cast<const uint2*>(planes + pstride)[i];
+          w[0] = __byte_perm(q0.x, q1.x, 0x5140); w[1] = __byte_perm(q0.x, q1.x, 0x7362);
+          w[2] = __byte_perm(q0.y, q1.y, 0x5140); w[3] = __byte_perm(q0.y, q1.y, 0x7362);
           }
         else
-          {
+          { // two elements: one 2-byte group of each of the 8 planes
+          uint32_t h[8];
 #pragma unroll
-          for (int e = 0; e < 2; ++e)
-#pragma unroll
-            for (int p = 0; p < 8; ++p) w[2 * e + (p >> 2)] |= (uint32_t)planes[p * pstride + i * 2 + e] << (8 * (p & 3));
+          for (int p = 0; p < 8; ++p) h[p] = reinterpret_cast<const uint16_t*>(planes + (size_t)p * pstride)[i];
+          const uint32_t a01 = __byte_perm(h[0], h[1], 0x5140), a23 = __byte_perm(h[2], h[3], 0x5140);   // e0.b0 e0.b1 e1.b0 e1.b1
+          const uint32_t a45 = __byte_perm(h[4], h[5], 0x5140), a67 = __byte_perm(h[6], h[7], 0x5140);
+          w[0] = __byte_perm(a01, a23, 0x5410); w[1] = __byte_perm(a45, a67, 0x5410);
+          w[2] = __byte_perm(a01, a23, 0x7632); w[3] = __byte_perm(a45, a67, 0x7632);
           }
         g4[i] = make_uint4(w[0], w[1], w[2], w[3]);
         }
