@@ -155,7 +155,14 @@ extern "C" int tb200_default_log2_chunk(int type, uint32_t count)
   const int codec = tb200_stream_layout(type, &w, &nc, &pc);
   (void)count;
   if (codec == 1) return w == 4 ? 9 : 8;     // 512 floats / 256 doubles per chunk (ratio cost <= 1 %)
-  if (codec == 2) return w == 8 ? 13 : 14;   // 16 KiB plane blocks (8 KiB for 8-byte elements: 8 planes share one CTA)
+  if (codec == 2)
+    {
+    // 16 KiB plane blocks (8 KiB for 8-byte elements: 8 planes share one CTA); TB200_LZ4_LOG2B overrides (experiments)
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("TB200_LZ4_LOG2B"); env = e ? atoi(e) : 0; }
+    if (env >= 8 && env <= 15) return w == 8 ? (env > 14 ? 14 : env) : env;
+    return w == 8 ? 13 : 14;
+    }
   return 0;
   }
 

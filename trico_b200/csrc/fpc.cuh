@@ -54,14 +54,28 @@ __host__ __device__ constexpr uint32_t fpc_chunk_bound(uint32_t values, int wbyt
 __device__ __forceinline__ int sig_bytes(uint32_t x) { return (39 - __clz((int)x)) >> 3; }
 __device__ __forceinline__ int sig_bytes(uint64_t x) { return (71 - __clzll((long long)x)) >> 3; }
 
+// byte store to shared memory through its 32-bit window address (one STS, no generic-address
+// arithmetic per store) or to a generic address
+template <bool OUT_SHARED>
+__device__ __forceinline__ void fpc_st8(uint8_t* gp, uint32_t sp, uint32_t off, uint32_t v)
+  {
+  if (OUT_SHARED) asm volatile("st.shared.u8 [%0], %1;" :: "r"(sp + off), "r"(v) : "memory");
+  else gp[off] = (uint8_t)v;
+  }
+
 // ---------------------------------------------------------------------------------------------
 // Warp-cooperative encoder of one chunk (or, with cnt = whole stream, of a reference v0 stream).
 //   src      values of this component: element j lives at src[j * stride]
-//   out      destination for the groups (code words + residual bytes); any address space
+//   out      destination for the groups (code words + residual bytes); shared memory when
+//            OUT_SHARED, else any address space
 //   T1, T2   per-warp predictor tables with (1<<e1) / (1<<e2) entries, zeroed here
 // Returns the number of bytes written.  All 32 lanes must call it.
+//
+// Byte offsets inside a window need no scan: the code words sit at fixed lanes (one per GROUP
+// values), so a lane's offset is HDR * (groups started so far) plus the residual bytes of the
+// lanes before it, and that sum is three (four) ballots of the bits of nb and population counts.
 // ---------------------------------------------------------------------------------------------
-template <typename W, typename SrcPtr>
+template <typename W, bool OUT_SHARED, typename SrcPtr>
 __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride, uint32_t cnt,
                                                     uint8_t* out, W* T1, W* T2, int e1, int e2)
   {
@@ -75,6 +89,9 @@ __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride,
   const int h = e2 >> 1;
   const uint32_t lowmask = (1u << h) - 1u;
   const uint32_t padlimit = (cnt + TR::GROUP - 1) / TR::GROUP * TR::GROUP;
+  const uint32_t out_s = OUT_SHARED ? (uint32_t)__cvta_generic_to_shared(out) : 0u;
+  const uint32_t gl = lane & (TR::GROUP - 1);               // position inside the group
+  const uint32_t hdr_before = TR::HDR * (lane / TR::GROUP + 1);   // code-word bytes up to and including this lane's group
   W carry_v = 0;
   uint32_t carry_ta = 0, carry_tb = 0;      // t[j-1], t[j-2] entering the window
   uint32_t obase = 0;
@@ -82,7 +99,8 @@ __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride,
   for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
     {
     const uint32_t j = i0 + lane;
-    const bool act = j < cnt;
+    const bool full = i0 + 32 <= cnt;       // warp-uniform: every lane holds a value
+    const bool act = full || j < cnt;
     const W v = act ? (W)src[(size_t)j * stride] : (W)0;
     W vprev = __shfl_up_sync(FULL, v, 1);
     if (lane == 0) vprev = carry_v;
@@ -91,7 +109,7 @@ __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride,
     const uint32_t c1 = (uint32_t)(vprev >> (TR::BITS - e1));
     const unsigned m1 = __match_any_sync(FULL, c1);
     const unsigned early1 = m1 & lt;
-    const int src1 = early1 ? 31 - __clz((int)early1) : (int)lane;
+    const int src1 = 31 - __clz((int)early1);                     // -1 when there is none (shfl result unused)
     const W p1s = __shfl_sync(FULL, v, src1);
     const W p1t = T1[c1];
     const W x1 = v ^ (early1 ? p1s : p1t);
@@ -106,7 +124,7 @@ __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride,
     const uint32_t c2 = ((tb & lowmask) << h) ^ ta;
     const unsigned m2 = __match_any_sync(FULL, c2);
     const unsigned early2 = m2 & lt;
-    const int src2 = early2 ? 31 - __clz((int)early2) : (int)lane;
+    const int src2 = 31 - __clz((int)early2);
     const W p2s = __shfl_sync(FULL, s, src2);
     const W p2t = T2[c2];
     const W x2 = v ^ (vprev + (early2 ? p2s : p2t));
@@ -115,47 +133,54 @@ __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride,
     const int n1 = sig_bytes(x1);
     int n2 = sig_bytes(x2); if (n2 == 0) n2 = 1;
     const bool use2 = (n1 >= 2) && (n2 < n1);
-    int code = use2 ? TR::BASE2 + n2 : n1;
-    int nb = use2 ? n2 : n1;
+    uint32_t code = use2 ? TR::BASE2 + n2 : n1;
+    uint32_t nb = use2 ? n2 : n1;
     W x = use2 ? x2 : x1;
-    if (!act)
-      { // pad slots of the last group: code 1 + one zero byte (fpc.c:196-204, :789-794)
-      const bool pad = j < padlimit;
-      code = pad ? 1 : 0; nb = pad ? 1 : 0; x = 0;
+    unsigned actmask = FULL;
+    if (!full)
+      { // last window: pad slots of the last group get code 1 + one zero byte (fpc.c:196-204, :789-794)
+      if (!act)
+        {
+        const bool pad = j < padlimit;
+        code = pad ? 1 : 0; nb = pad ? 1 : 0; x = 0;
+        }
+      actmask = __ballot_sync(FULL, act);
       }
 
     // table update: the last active element of every context wins (what a serial pass leaves)
-    const unsigned actmask = __ballot_sync(FULL, act);
     if (act && ((m1 & gt & actmask) == 0)) T1[c1] = v;
     if (act && ((m2 & gt & actmask) == 0)) T2[c2] = s;
 
-    // code word of this lane's group
-    uint32_t bc = (uint32_t)code << (TR::CBITS * (lane & (TR::GROUP - 1)));
+    // code word of this lane's group (every lane of the group ends up with it)
+    uint32_t bc = code << (TR::CBITS * gl);
 #pragma unroll
     for (int o = 1; o < TR::GROUP; o <<= 1) bc |= __shfl_xor_sync(FULL, bc, o);
-    const bool leader = ((lane & (TR::GROUP - 1)) == 0) && (j < padlimit);
 
-    // byte offsets: exclusive scan of (header bytes of a group leader + residual bytes)
-    const uint32_t contrib = (uint32_t)nb + (leader ? TR::HDR : 0);
-    uint32_t incl = contrib;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
+    // byte offsets from the bit planes of nb
+    const unsigned b0 = __ballot_sync(FULL, nb & 1u), b1 = __ballot_sync(FULL, nb & 2u), b2 = __ballot_sync(FULL, nb & 4u);
+    uint32_t pre = __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+    uint32_t sum = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+    if (TR::WBYTES == 8)
       {
-      const uint32_t up = __shfl_up_sync(FULL, incl, o);
-      if (lane >= (unsigned)o) incl += up;
+      const unsigned b3 = __ballot_sync(FULL, nb & 8u);
+      pre += 8u * __popc(b3 & lt); sum += 8u * __popc(b3);
       }
-    uint8_t* p = out + obase + (incl - contrib);
-    if (leader)
+    const uint32_t ngroups = full ? 32u / TR::GROUP : (min(cnt - i0, 32u) + TR::GROUP - 1) / TR::GROUP;
+    // code word: byte k of group g is written by lane g*GROUP + k at (bytes before the group) + k
+    const uint32_t gpre = __shfl_sync(FULL, pre, lane & ~(TR::GROUP - 1));
+    if (gl < (uint32_t)TR::HDR && j < padlimit)
+      fpc_st8<OUT_SHARED>(out, out_s, obase + hdr_before - TR::HDR + gpre + gl, (bc >> (8 * (TR::HDR - 1 - gl))) & 0xffu);
+    // residual bytes, most significant first
+    if (nb)
       {
-      if (TR::HDR == 3) { p[0] = (uint8_t)(bc >> 16); p[1] = (uint8_t)(bc >> 8); p[2] = (uint8_t)bc; }
-      else              { p[0] = (uint8_t)bc; }
-      p += TR::HDR;
-      }
+      const uint32_t at = obase + hdr_before + pre;
+      const W xs = x << (8 * (TR::WBYTES - nb));                  // left-justified: byte b is at a fixed position
 #pragma unroll
-    for (int b = 0; b < TR::WBYTES; ++b)
-      if (b < nb) p[b] = (uint8_t)(x >> (8 * (nb - 1 - b)));
+      for (int b = 0; b < TR::WBYTES; ++b)
+        if ((uint32_t)b < nb) fpc_st8<OUT_SHARED>(out, out_s, at + b, (uint32_t)(xs >> (8 * (TR::WBYTES - 1 - b))) & 0xffu);
+      }
 
-    obase += __shfl_sync(FULL, incl, 31);
+    obase += TR::HDR * ngroups + sum;
     carry_v = __shfl_sync(FULL, v, 31);
     carry_tb = __shfl_sync(FULL, t, 30);
     carry_ta = __shfl_sync(FULL, t, 31);
@@ -240,7 +265,7 @@ fpc_encode_kernel(const FpcEncodeArgs a)
     const uint32_t cnt = (uint32_t)((a.n - lo < S) ? (a.n - lo) : S);
     W* T1 = tables + (size_t)warp * ((1u << a.e1) + (1u << a.e2));
     W* T2 = T1 + (1u << a.e1);
-    nbytes = fpc_encode_warp<W>(tile_in + (size_t)kk * S * NCOMP + c, NCOMP, cnt, stage + (size_t)warp * slot, T1, T2, a.e1, a.e2);
+    nbytes = fpc_encode_warp<W, true>(tile_in + (size_t)kk * S * NCOMP + c, NCOMP, cnt, stage + (size_t)warp * slot, T1, T2, a.e1, a.e2);
     }
   if (lane == 0) sh_size[warp] = nbytes;
   __syncthreads();
@@ -330,7 +355,7 @@ fpc_encode_legacy_kernel(const FpcLegacyEncodeArgs a)
     nb = TR::HDR + TR::GROUP;
     }
   else
-    nb = fpc_encode_warp<W>(src, a.stride, a.n, out + 5, T1, T2, a.e1, a.e2);
+    nb = fpc_encode_warp<W, false>(src, a.stride, a.n, out + 5, T1, T2, a.e1, a.e2);
   if (lane == 0) a.nbytes[c] = nb + 5;
   }
 

@@ -27,8 +27,17 @@ __device__ __forceinline__ uint32_t smem_read32(const uint8_t* base, uint32_t po
   return __funnelshift_r(w[0], w[1], (pos & 3u) * 8u);
   }
 
+// 16 bytes at an arbitrary shared-memory position (the word after the last byte must be readable)
+__device__ __forceinline__ uint4 smem_read128(const uint8_t* base, uint32_t pos)
+  {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (pos >> 2);
+  const unsigned sh = (pos & 3u) * 8u;
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+  }
+
 // warp copy of n literal bytes src[s..s+n) (shared memory) to dst (any alignment, any space);
-// long runs move as 32-bit words (128 bytes per warp instruction)
+// long runs move as 16-byte vectors (512 bytes per warp instruction), four in flight per lane
 template <typename DstPtr>
 __device__ __forceinline__ void lz4_copy_from_smem(DstPtr dst, const uint8_t* src, uint32_t s, uint32_t n)
   {
@@ -38,12 +47,28 @@ __device__ __forceinline__ void lz4_copy_from_smem(DstPtr dst, const uint8_t* sr
     for (uint32_t i = lane; i < n; i += 32) dst[i] = src[s + i];
     return;
     }
-  const uint32_t head = (4u - ((uint32_t)reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+  const uint32_t head = (16u - ((uint32_t)reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
   if (lane < head) dst[lane] = src[s + lane];
-  const uint32_t nw = (n - head) >> 2;
-  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-  for (uint32_t i = lane; i < nw; i += 32) dw[i] = smem_read32(src, s + head + 4 * i);
-  const uint32_t done = head + (nw << 2);
+  const uint32_t nv = (n - head) >> 4;
+  uint4* dv = reinterpret_cast<uint4*>(dst + head);
+  constexpr int UN = 4;
+  for (uint32_t i0 = 0; i0 < nv; i0 += 32 * UN)
+    {
+    uint4 v[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      {
+      const uint32_t i = i0 + lane + 32 * u;
+      if (i < nv) v[u] = smem_read128(src, s + head + 16u * i);
+      }
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      {
+      const uint32_t i = i0 + lane + 32 * u;
+      if (i < nv) dv[i] = v[u];
+      }
+    }
+  const uint32_t done = head + (nv << 4);
   if (done + lane < n) dst[done + lane] = src[s + done + lane];
   }
 
@@ -71,7 +96,7 @@ __device__ __forceinline__ uint32_t lz4_emit(DstPtr dst, uint32_t op, const uint
   return op;
   }
 
-constexpr uint32_t LZ4_SRC_PAD = 176;    // zeroed bytes the compressor may read past the block end
+constexpr uint32_t LZ4_SRC_PAD = 560;    // zeroed bytes the compressor may read past the block end (512-byte match extension steps)
 
 // Compresses src[0..n) (shared memory, LZ4_SRC_PAD zero bytes readable past n) into dst.
 // `table` = (1 << HLOG) u16 entries of shared memory private to the warp.  n <= 65535.
@@ -100,24 +125,36 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
       const uint32_t h = (seq * 2654435761u) >> (32 - HLOG);
       uint32_t cand = table[h];
       bool ok = valid && cand < q && smem_read32(src, cand) == seq;
-      // repeats inside the window are invisible to the table (it is read before this window is
-      // inserted): find them by comparing the 4-byte sequences of the lanes directly
-      const unsigned twins = __match_any_sync(FULL, valid ? seq : (0x5a000000u ^ lane)) & lt & __ballot_sync(FULL, valid);
-      if (valid && twins)
+      // Repeats inside the window are invisible to the table (it is read before this window is
+      // inserted): find them by comparing the 4-byte sequences of the lanes directly.  Only while
+      // the scan is dense: once it accelerates (nothing matched for 64 positions) the data is not
+      // periodic at this scale, and match.any over 32 distinct values is the slowest instruction here.
+      if (stride == 1u)
         {
-        const uint32_t near = p + (31u - (uint32_t)__clz((int)twins)) * stride;
-        if (!ok || near > cand) { cand = near; ok = true; }
+        const unsigned twins = __match_any_sync(FULL, valid ? seq : (0x5a000000u ^ lane)) & lt & __ballot_sync(FULL, valid);
+        if (valid && twins)
+          {
+          const uint32_t near = p + (31u - (uint32_t)__clz((int)twins));
+          if (!ok || near > cand) { cand = near; ok = true; }
+          }
         }
       const unsigned mask = __ballot_sync(FULL, ok);
       const int f = mask ? __ffs((int)mask) - 1 : 31;
       // Insert the tested positions up to the chosen match only: later ones are scanned again
       // and must still see their older candidates.  Among lanes sharing a bucket the highest
-      // position wins, so the table (and the output) is deterministic.
+      // position must win, so that the table (and the output) is deterministic: every lane
+      // stores, then the losers of a bucket (they read back a lower position) store again.
       const bool ins = valid && (int)lane <= f;
-      const unsigned same = __match_any_sync(FULL, ins ? h : (0x80000000u | lane));
       __syncwarp();
-      if (ins && (same & gt) == 0) table[h] = (uint16_t)q;
+      if (ins) table[h] = (uint16_t)q;
       __syncwarp();
+      for (;;)
+        {
+        const bool lost = ins && table[h] < (uint16_t)q;
+        if (!__any_sync(FULL, lost)) break;
+        if (lost) table[h] = (uint16_t)q;
+        __syncwarp();
+        }
       if (mask == 0) { p += 32u * stride; attempts += 32; continue; }
       attempts = 0;
       uint32_t mq = p + (uint32_t)f * stride;
@@ -130,24 +167,37 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
         const uint32_t back = neb ? (uint32_t)__ffs((int)neb) - 1u : 32u;
         mq -= back; mc -= back;
         }
-      // forward extension, 4 bytes per lane = 128 bytes per step; bytes past the block end are
-      // zero padding and the result is clamped to the last position a match may cover
+      // forward extension: a first step of 4 bytes per lane (most matches end inside 128 bytes),
+      // then 16 bytes per lane = 512 bytes per step; bytes past the block end are zero padding and
+      // the result is clamped to the last position a match may cover
       const uint32_t maxlen = matchlimit - mq;
       uint32_t len = LZ4_MINMATCH;
-      for (;;)
         {
         const uint32_t x = smem_read32(src, mq + len + 4 * lane) ^ smem_read32(src, mc + len + 4 * lane);
         const unsigned ne = __ballot_sync(FULL, x != 0);
-        if (ne == 0)
+        if (ne)
+          {
+          const int fl = __ffs((int)ne) - 1;
+          const uint32_t xf = __shfl_sync(FULL, x, fl);
+          len += 4u * (uint32_t)fl + (((uint32_t)__ffs((int)xf) - 1u) >> 3);
+          }
+        else
           {
           len += 128;
-          if (len >= maxlen) break;
-          continue;
+          while (len < maxlen)
+            {
+            const uint4 va = smem_read128(src, mq + len + 16 * lane), vb = smem_read128(src, mc + len + 16 * lane);
+            const uint32_t x0 = va.x ^ vb.x, x1 = va.y ^ vb.y, x2 = va.z ^ vb.z, x3 = va.w ^ vb.w;
+            const unsigned nw = __ballot_sync(FULL, (x0 | x1 | x2 | x3) != 0);
+            if (nw == 0) { len += 512; continue; }
+            const int fl = __ffs((int)nw) - 1;
+            const uint32_t xw = x0 ? x0 : x1 ? x1 : x2 ? x2 : x3;
+            const uint32_t wi = x0 ? 0u : x1 ? 1u : x2 ? 2u : 3u;
+            const uint32_t mine = 4u * wi + (((uint32_t)__ffs((int)xw) - 1u) >> 3);
+            len += 16u * (uint32_t)fl + __shfl_sync(FULL, mine, fl);
+            break;
+            }
           }
-        const int fl = __ffs((int)ne) - 1;
-        const uint32_t xf = __shfl_sync(FULL, x, fl);
-        len += 4u * (uint32_t)fl + (((uint32_t)__ffs((int)xf) - 1u) >> 3);
-        break;
         }
       if (len > maxlen) len = maxlen;
       op = lz4_emit(dst, op, src, anchor, mq - anchor, mq - mc, len);
@@ -602,15 +652,6 @@ __device__ __forceinline__ uint32_t lz4_read_ext(const uint8_t* buf, uint32_t& i
     ip += (uint32_t)e + 1u;
     return add;
     }
-  }
-
-// 16 bytes at an arbitrary shared-memory position (needs the word after the last byte readable)
-__device__ __forceinline__ uint4 smem_read128(const uint8_t* base, uint32_t pos)
-  {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (pos >> 2);
-  const unsigned sh = (pos & 3u) * 8u;
-  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
   }
 
 // Warp copy inside one shared-memory buffer, dst and src arbitrary.  FORWARD_OVERLAP: dst < src
