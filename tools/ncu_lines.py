@@ -59,7 +59,14 @@ while i < len(rows):
             continue
         done.add(kname)
         # find the matching nvdisasm section by instruction count + mangled-name hint
-        cands = [(n, s) for n, s in sections.items() if len(s) == len(body)]
+        import re as _re
+        base = _re.sub(r"^void ", "", kname).split("<")[0].split("(")[0].split("::")[-1]
+        cands = [(n, s) for n, s in sections.items() if len(s) == len(body) and base in n]
+        if len(cands) > 1:
+            # several template instances of the same size: keep the one whose opcodes line up
+            def score(sec):
+                return sum(1 for r, (a, ins, ln) in zip(body, sec) if r[1].split()[0:1] == ins.split()[0:1] or ins.split()[0] in r[1])
+            cands.sort(key=lambda c: -score(c[1]))
         if not cands:
             print(f"## {kname}: no disassembly with {len(body)} instructions (library differs from the profiled build?)"); continue
         sec = cands[0][1]

@@ -379,7 +379,7 @@ struct Lz4EncodeArgs
   uint32_t* ticket;        // chunk ticket, zeroed
   };
 
-constexpr int LZ4_HLOG = 12;     // 4096 u16 entries = 8 KiB per warp
+constexpr int LZ4_HLOG = 10;     // default: 1024 u16 entries = 2 KiB per warp (12 resident warps per SM with 16 KiB blocks)
 template <int WB> struct Lz4Cta { static constexpr int WARPS = WB > 4 ? WB : 4; };
 
 // keeps byte `p` of every WB-byte element of one 16-byte vector; returns them packed LSB first
@@ -402,7 +402,7 @@ __device__ __forceinline__ uint32_t plane_bytes(const uint4 v, uint32_t p)
   return ((a >> (8 * (p & 3))) & 0xffu) | (((b >> (8 * (p & 3))) & 0xffu) << 8);
   }
 
-template <int WB>
+template <int WB, int HLOG>
 __global__ void __launch_bounds__(Lz4Cta<WB>::WARPS * 32)
 lz4_encode_kernel(const Lz4EncodeArgs a)
   {
@@ -412,7 +412,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
   const uint32_t pstride = B + LZ4_SRC_PAD;                          // block buffer padded for read-ahead
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
   uint8_t* buf = smem_raw + (size_t)warp * pstride;
-  uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WARPS * pstride) + ((size_t)warp << LZ4_HLOG);
+  uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WARPS * pstride) + ((size_t)warp << HLOG);
   const uint64_t nchunks = (uint64_t)a.nranges * WB;
 
   // tickets are taken one chunk ahead so the next range can be pulled towards L2 while this
@@ -496,7 +496,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
     __syncwarp();
 
     // 2. compress into this chunk's slot
-    const uint32_t nbytes = lz4_compress_warp<LZ4_HLOG>(buf, cnt, a.scratch + g * a.slot, table);
+    const uint32_t nbytes = lz4_compress_warp<HLOG>(buf, cnt, a.scratch + g * a.slot, table);
     if (lane == 0)
       {
       uint8_t* sz = a.sizes + 2 * g;
@@ -632,8 +632,9 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
 // and are generated from their first 64 bytes with independent 16-byte reads and stores.
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr uint32_t lz4_inplace_stride(uint32_t B)
-  { // output + in-place margin of the largest block + 32 bytes of slack for alignment and word read-ahead
-  return ((B + (lz4_block_bound(B) >> 8) + 32u + 48u) + 15u) & ~15u;
+  { // output + in-place margin of the largest block + 16 (vector-store overshoot) + 15 (alignment of
+    // the staged block) + 32 readable bytes behind the block + slack
+  return ((B + (lz4_block_bound(B) >> 8) + 32u + 16u + 15u + 32u + 17u) + 15u) & ~15u;
   }
 
 // reads a length continuation (bytes of 255 terminated by a byte < 255, lz4.c:1629-1649) at ip;
@@ -705,107 +706,250 @@ __device__ __forceinline__ void lz4_smem_move(uint8_t* buf, uint32_t dst, uint32
     }
   }
 
+// ceil(2^32 / o) for o = 2..32: t mod o = t - o * umulhi(t, inv) is exact for t < 2^16.  Offset 1
+// would need 2^32; its entry is 0 and the result is masked to 0 (every index of a run is 0).
+__constant__ uint32_t c_lz4_inv[33] = { 0x00000000u, 0x00000000u, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2aaaaaabu, 0x24924925u, 0x20000000u, 0x1c71c71du, 0x1999999au, 0x1745d175u, 0x15555556u, 0x13b13b14u, 0x12492493u, 0x11111112u, 0x10000000u, 0x0f0f0f10u, 0x0e38e38fu, 0x0d79435fu, 0x0ccccccdu, 0x0c30c30du, 0x0ba2e8bbu, 0x0b21642du, 0x0aaaaaabu, 0x0a3d70a4u, 0x09d89d8au, 0x097b425fu, 0x0924924au, 0x08d3dcb1u, 0x08888889u, 0x08421085u, 0x08000000u };
+
+// One match, produced by the whole warp.  opm = output position of the match.  Exact: nothing is
+// written at or past opm + mlen (the next sequence's literals are already in place).
+__device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint32_t offset, uint32_t mlen)
+  {
+  const unsigned lane = lane_id();
+  if (offset <= 32u && mlen > offset)
+    { // Short period (runs, interleaved index patterns).  The first 64 output bytes are written
+      // byte-wise (lane l: bytes l and l+32 of the pattern); they then serve as a look-up table:
+      // the 16 bytes at any later position x are the 16 bytes at opm + (x - opm) mod offset, so the
+      // rest of the match is produced with independent 16-byte reads and aligned stores, no further
+      // synchronisation and no dependence on the match length.
+    const uint8_t* ms = buf + opm - offset;
+    const uint32_t inv = c_lz4_inv[offset];
+    const uint32_t keep = offset == 1u ? 0u : 0xffffffffu;
+    auto modo = [&](uint32_t t) { return (t - offset * __umulhi(t, inv)) & keep; };
+    const uint32_t q0 = ms[modo(lane)], q1 = ms[modo(lane + 32u)];
+    if (lane < mlen) buf[opm + lane] = (uint8_t)q0;
+    if (lane + 32u < mlen) buf[opm + lane + 32u] = (uint8_t)q1;
+    if (mlen > 64u)
+      {
+      __syncwarp();
+      const uint32_t end = opm + mlen;
+      uint32_t xa = (opm + 64u) & ~15u;                                  // aligned, inside the table: rewriting [xa, opm+64) is harmless
+      const uint32_t nv = (end - xa) >> 4;
+      const uint32_t t0 = xa - opm;
+      constexpr int UN = 4;
+      for (uint32_t i0 = 0; i0 < nv; i0 += 32 * UN)
+        {
+        uint4 v[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) v[u] = smem_read128(buf, opm + modo(t0 + 16u * (i0 + lane + 32 * u)));
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+          {
+          const uint32_t i = i0 + lane + 32 * u;
+          if (i < nv) *reinterpret_cast<uint4*>(buf + xa + 16u * i) = v[u];
+          }
+        }
+      const uint32_t done = xa + (nv << 4);
+      if (done + lane < end) buf[done + lane] = buf[opm + modo(done - opm + lane)];
+      }
+    }
+  else if (offset >= mlen)
+    lz4_smem_move<false>(buf, opm, opm - offset, mlen);
+  else
+    { // periodic with a long period: grow by copying everything available, distance doubling
+    uint32_t copied = 0, dist = offset;
+    while (copied < mlen)
+      {
+      const uint32_t chunk = min(dist, mlen - copied);
+      lz4_smem_move<false>(buf, opm + copied, opm + copied - dist, chunk);
+      copied += chunk;
+      if (dist < 4096u) dist <<= 1;               // [opm-offset, opm+copied) is periodic: 2*dist <= offset + copied
+      __syncwarp();
+      }
+    }
+  }
+
 // Decodes the block buf[ip, iend) into buf[0, cap).  Returns the bytes produced or 0xffffffff.
-__device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip, uint32_t iend, uint32_t cap)
+//
+// A block is a chain of sequences whose positions are only known by walking the tokens, but the
+// walk itself touches nothing but a few length bytes.  So the decoder works in batches of up to
+// 32 sequences:
+//   1. PARSE   the warp walks the tokens; lane s keeps the descriptor of sequence s of the batch
+//              (literal source and length, output position, offset, match length)
+//   2. LITERALS of all sequences of the batch at once: lane s copies its own short run byte by
+//              byte (runs never overlap each other's sources); long runs move warp-wide
+//   3. MATCHES in order.  Up to four at a time, eight lanes each, when they cannot see each
+//              other's output (source inside the sequence's own literals or below the first match
+//              of the group); otherwise one at a time with the whole warp.
+// Output never passes the unread input (LZ4's in-place margin), so deferring the copies of a
+// batch is safe: everything a batch writes lies below the next batch's first token.
+// The checks are the memory-safety ones (every access stays inside the buffer for any input); a
+// malformed block is reported through the byte count it produces.
+#define LZ4_DEC_T(i) do { if (dbg && lane == 0) { const long long t__ = clock64(); atomicAdd(dbg + (i), (unsigned long long)(t__ - t_dec)); t_dec = t__; } } while (0)
+__device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip, uint32_t iend, uint32_t cap, unsigned long long* dbg = nullptr)
   {
   const unsigned lane = lane_id();
   uint32_t op = 0;
   if (ip >= iend) return 0xffffffffu;
-  for (;;)
+  bool finished = false;
+  long long t_dec = dbg ? clock64() : 0;
+  while (!finished)
     {
-    if (ip >= iend) return 0xffffffffu;
-    // the token and the 31 bytes behind it in one read: short sequences need nothing else
-    const uint32_t b = (ip + lane < iend) ? buf[ip + lane] : 0u;
-    const uint32_t token = __shfl_sync(FULL, b, 0);
-    uint32_t lit = token >> 4;
-    uint32_t offset = 0;
-    bool have_offset = false;
-    if (lit < 15u)
-      { // literals (and, unless this is the last sequence, the offset) are already in registers
-      if (ip + 1u + lit > iend || op + lit > cap || op > ip + 1u) return 0xffffffffu;     // writes must stay behind the unread input
-      __syncwarp();
-      if (lane >= 1u && lane <= lit) buf[op + lane - 1u] = (uint8_t)b;
-      offset = __shfl_sync(FULL, b, (lit + 1u) & 31u) | (__shfl_sync(FULL, b, (lit + 2u) & 31u) << 8);
-      have_offset = true;
-      ip += 1u + lit; op += lit;
-      }
-    else
+    // ---- 1. parse ----
+    LZ4_DEC_T(3);
+    uint32_t d_src = 0, d_lit = 0, d_op = 0, d_off = 1, d_mlen = 0;
+    uint32_t ns = 0;
+    while (ns < 32u)
       {
-      ip += 1;
-      if (lit == 15u) lit += lz4_read_ext(buf, ip, iend);
-      if (ip + lit > iend || op + lit > cap || op > ip) return 0xffffffffu;
-      lz4_smem_move<true>(buf, op, ip, lit);
-      ip += lit; op += lit;
-      }
-    if (ip >= iend) break;                          // last sequence has no match part
-    if (ip + 2u > iend) return 0xffffffffu;
-    if (!have_offset) offset = (uint32_t)buf[ip] | ((uint32_t)buf[ip + 1] << 8);
-    ip += 2;
-    uint32_t mlen = token & 15u;
-    if (mlen == 15u) mlen += lz4_read_ext(buf, ip, iend);
-    mlen += LZ4_MINMATCH;
-    // the match may not run over unread input (cannot happen for blocks that respect the margin)
-    if (offset == 0 || offset > op || op + mlen > cap || op + mlen > ip) return 0xffffffffu;
-    __syncwarp();                                   // literals of this sequence are visible
-    if (offset >= mlen)
-      lz4_smem_move<false>(buf, op, op - offset, mlen);
-    else if (offset > 32u)
-      { // periodic with a long period: grow by copying everything available, distance doubling
-      uint32_t copied = 0, dist = offset;
-      while (copied < mlen)
+      if (ip >= iend) return 0xffffffffu;
+      // the token and the 31 bytes behind it in one read (32 readable bytes follow every block)
+      const uint32_t b = buf[ip + lane];
+      const uint32_t token = __shfl_sync(FULL, b, 0);
+      uint32_t lit = token >> 4, ml = token & 15u, offset = 1, src, mlen = 0;
+      bool last;
+      if (lit < 15u)
         {
-        const uint32_t chunk = min(dist, mlen - copied);
-        lz4_smem_move<false>(buf, op + copied, op + copied - dist, chunk);
-        copied += chunk;
-        if (dist < 4096u) dist <<= 1;               // [op-offset, op+copied) is periodic: 2*dist <= offset + copied
+        const uint32_t e = lit + 1u;                                // index of the offset's low byte inside b
+        src = ip + 1u;
+        ip += e;
+        last = ip >= iend;
+        if (!last)
+          {
+          offset = __shfl_sync(FULL, b, e) | (__shfl_sync(FULL, b, e + 1u) << 8);
+          ip += 2;
+          if (ml == 15u)
+            { // continuation bytes start at index e+2 of b
+            const unsigned m = __ballot_sync(FULL, b != 255u) >> (e + 2u);
+            if (m)
+              {
+              const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+              ml += 255u * k + __shfl_sync(FULL, b, e + 2u + k);
+              ip += k + 1u;
+              }
+            else
+              {
+              ml += 255u * (30u - e); ip += 30u - e;
+              ml += lz4_read_ext(buf, ip, iend);
+              }
+            }
+          }
+        }
+      else
+        {
+        ip += 1;
+        lit += lz4_read_ext(buf, ip, iend);
+        src = ip;
+        if (lit > iend || ip + lit > iend) return 0xffffffffu;
+        ip += lit;
+        last = ip >= iend;
+        if (!last)
+          {
+          offset = (uint32_t)buf[ip] | ((uint32_t)buf[ip + 1] << 8);
+          ip += 2;
+          if (ml == 15u) ml += lz4_read_ext(buf, ip, iend);
+          }
+        }
+      if (!last) mlen = ml + LZ4_MINMATCH;
+      // literals copy forward in place (dst <= src); everything stays inside [0, cap) and [.., iend]
+      if (ip > iend || mlen > cap || lit > cap || op + lit + mlen > cap || op > src || (!last && (offset == 0 || offset > op + lit))) return 0xffffffffu;
+      if (lane == ns) { d_src = src; d_lit = lit; d_op = op; d_off = offset; d_mlen = mlen; }
+      op += lit + mlen;
+      ++ns;
+      if (last) { finished = true; break; }
+      }
+
+    LZ4_DEC_T(0);
+    // ---- 2. literals ----
+    // A later run's destination may overlap an earlier run's source (output trails the input by
+    // less than a sequence where the data compresses poorly), so nothing is written before every
+    // source has been read: short runs (<= 16 bytes) are fetched into registers by all lanes at
+    // once, long runs then move one after the other in stream order with the whole warp, and the
+    // short runs are stored last.
+    const bool mine = lane < ns;
+      {
+      const bool shortrun = mine && d_lit <= 16u;
+      uint4 lv = make_uint4(0, 0, 0, 0);
+      if (shortrun && d_lit) lv = smem_read128(buf, d_src);
+      __syncwarp();
+      unsigned longs = __ballot_sync(FULL, mine && d_lit > 16u);
+      while (longs)
+        {
+        const int sq = __ffs((int)longs) - 1;
+        longs &= longs - 1u;
+        lz4_smem_move<true>(buf, __shfl_sync(FULL, d_op, sq), __shfl_sync(FULL, d_src, sq), __shfl_sync(FULL, d_lit, sq));
         __syncwarp();
         }
-      }
-    else
-      { // Short period (runs, interleaved index patterns).  The first 64 output bytes are written
-        // byte-wise (lane l: bytes l and l+32 of the pattern); they then serve as a look-up table:
-        // the 16 bytes at any later position x are the 16 bytes at op + (x - op) mod offset, so the
-        // rest of the match is produced with independent 16-byte reads and stores, no further
-        // synchronisation and no dependence on the match length.
-      const uint8_t* ms = buf + op - offset;
-      // t mod offset by multiplication: inv = ceil(2^32 / offset) gives exact quotients for t < 2^16
-      // (offset 1 would need 2^32: there every index is 0 and inv = 0 with the mask below does that)
-      const uint32_t inv = offset == 1u ? 0u : 0xffffffffu / offset + 1u;
-      const uint32_t keep = offset == 1u ? 0u : 0xffffffffu;
-      auto modo = [&](uint32_t t) { return (t - offset * __umulhi(t, inv)) & keep; };
-      const uint32_t r0 = modo(lane), r1 = modo(lane + 32u);
-      const uint32_t q0 = ms[r0], q1 = ms[r1];
-      __syncwarp();
-      if (lane < mlen) buf[op + lane] = (uint8_t)q0;
-      if (lane + 32u < mlen) buf[op + lane + 32u] = (uint8_t)q1;
-      __syncwarp();
-      if (mlen > 64u)
+      if (shortrun)
         {
-        const uint32_t from = op + 64u, end = op + mlen;
-        const uint32_t xa = (from + 15u) & ~15u;
-        if (xa >= end)
-          {
-          if (from + lane < end) { const uint32_t t = 64u + lane; buf[from + lane] = buf[op + modo(t)]; }
-          }
-        else
-          {
-          const uint32_t head = xa - from;
-          if (lane < head) { const uint32_t t = 64u + lane; buf[from + lane] = buf[op + modo(t)]; }
-          const uint32_t nv = (end - xa) >> 4;
-          const uint32_t t0 = xa - op;
-          for (uint32_t i = lane; i < nv; i += 32)
-            {
-            const uint32_t t = t0 + 16u * i;
-            const uint32_t sft = modo(t);
-            *reinterpret_cast<uint4*>(buf + xa + 16u * i) = smem_read128(buf, op + sft);
-            }
-          const uint32_t done = xa + (nv << 4);
-          if (done + lane < end) { const uint32_t t = done - op + lane; buf[done + lane] = buf[op + modo(t)]; }
-          }
+        const uint32_t w[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+        for (uint32_t j = 0; j < 16; ++j)
+          if (j < d_lit) buf[d_op + j] = (uint8_t)(w[j >> 2] >> (8u * (j & 3u)));
         }
       }
-    op += mlen;
     __syncwarp();
+    LZ4_DEC_T(1);
+
+    // ---- 3. matches ----
+    const uint32_t nm = finished ? ns - 1u : ns;                      // the block's last sequence has no match
+    const uint32_t grp = lane >> 3, li = lane & 7u;
+    uint32_t s0 = 0;
+    while (s0 < nm)
+      {
+      // candidate group: sequences s0 .. s0+3, eight lanes each
+      const uint32_t q = s0 + grp;
+      const uint32_t g_lit = __shfl_sync(FULL, d_lit, q & 31u), g_off = __shfl_sync(FULL, d_off, q & 31u);
+      const uint32_t g_mlen = __shfl_sync(FULL, d_mlen, q & 31u);
+      const uint32_t g_opm = __shfl_sync(FULL, d_op, q & 31u) + g_lit;
+      const uint32_t first_opm = __shfl_sync(FULL, g_opm, 0);
+      const bool is_lut = g_off <= 32u && g_mlen > g_off;
+      const bool is_small_move = g_off >= g_mlen && g_mlen <= 128u;
+      const uint32_t need = g_off < g_mlen ? g_off : g_mlen;          // source bytes that must already exist
+      const bool indep = grp == 0 || g_off <= g_lit || g_opm - g_off + need <= first_opm;
+      const bool can = q < nm && g_mlen <= 2048u && (is_lut || is_small_move) && indep;
+      const unsigned canmask = __ballot_sync(FULL, can);
+      // number of leading groups that can run together
+      const uint32_t together = (canmask & 1u) == 0 ? 0u : (canmask & 0x100u) == 0 ? 1u : (canmask & 0x10000u) == 0 ? 2u : (canmask & 0x1000000u) == 0 ? 3u : 4u;
+      if (together >= 2u)
+        {
+        const bool on = grp < together;
+        const uint32_t inv = c_lz4_inv[on && is_lut ? g_off : 2u];
+        const uint32_t keep = g_off == 1u ? 0u : 0xffffffffu;
+        auto modo = [&](uint32_t t) { return (t - g_off * __umulhi(t, inv)) & keep; };
+        if (on && !is_lut)
+          for (uint32_t t = li; t < g_mlen; t += 8) buf[g_opm + t] = buf[g_opm - g_off + t];
+        if (on && is_lut)
+          {
+          const uint8_t* ms = buf + g_opm - g_off;
+          uint32_t pat[8];
+#pragma unroll
+          for (uint32_t j = 0; j < 8; ++j) pat[j] = ms[modo(8u * li + j)];
+#pragma unroll
+          for (uint32_t j = 0; j < 8; ++j) if (8u * li + j < g_mlen) buf[g_opm + 8u * li + j] = (uint8_t)pat[j];
+          }
+        __syncwarp();
+        if (on && is_lut && g_mlen > 64u)
+          {
+          const uint32_t end = g_opm + g_mlen;
+          const uint32_t xa = (g_opm + 64u) & ~15u;
+          const uint32_t nv = (end - xa) >> 4;
+          const uint32_t t0 = xa - g_opm;
+          for (uint32_t i = li; i < nv; i += 8)
+            *reinterpret_cast<uint4*>(buf + xa + 16u * i) = smem_read128(buf, g_opm + modo(t0 + 16u * i));
+          const uint32_t done = xa + (nv << 4);
+          for (uint32_t t = done + li; t < end; t += 8) buf[t] = buf[g_opm + modo(t - g_opm)];
+          }
+        __syncwarp();
+        s0 += together;
+        }
+      else
+        {
+        const uint32_t w_lit = __shfl_sync(FULL, d_lit, s0 & 31u);
+        lz4_match_warp(buf, __shfl_sync(FULL, d_op, s0 & 31u) + w_lit, __shfl_sync(FULL, d_off, s0 & 31u), __shfl_sync(FULL, d_mlen, s0 & 31u));
+        __syncwarp();
+        s0 += 1;
+        }
+      }
+    LZ4_DEC_T(2);
     }
   return op;
   }
@@ -830,7 +974,10 @@ struct Lz4DecodeArgs
   uint64_t* desc;
   uint32_t* ticket;
   uint32_t* status;        // set to 1 if any block was malformed
+  unsigned long long* dbg; // phase-cycle counters (experiments; nullptr in production)
   };
+
+#define TB200_PH(i) do { if (a.dbg && lane == 0) { const long long t__ = clock64(); atomicAdd(a.dbg + (i) * 4 + (warp & 3), (unsigned long long)(t__ - t_ph)); t_ph = t__; } } while (0)
 
 template <int WB>
 __global__ void __launch_bounds__(WB * 32)
@@ -840,36 +987,59 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
   const uint32_t B = 1u << a.log2B;
   const uint32_t pstride = lz4_inplace_stride(B);
   uint8_t* planes = smem_raw;
-  __shared__ uint32_t sh_tile;
-  __shared__ uint64_t sh_base;
+  // the tile being decoded and the one after it: warp 0 fetches the next tile's ticket, sizes and
+  // base offset (look-back) while the slower planes are still decoding, so that chain of global
+  // round trips is off the critical path; it also pulls the next tile's blocks towards L2
+  __shared__ uint32_t sh_tile[2];
+  __shared__ uint64_t sh_base[2];
+  __shared__ uint32_t sh_sz[2][WB];
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
 
+  auto fetch_tile = [&](int slot)
+    { // warp 0 only, all lanes
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1u);
+    t = __shfl_sync(FULL, t, 0);
+    uint32_t mysz = 0;
+    if (t < a.nranges && lane < WB)
+      {
+      const uint8_t* sz = a.sizes + 2 * ((uint64_t)t * WB + lane);
+      mysz = (uint32_t)sz[0] | ((uint32_t)sz[1] << 8);
+      }
+    uint32_t agg = mysz;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) agg += __shfl_xor_sync(FULL, agg, o);      // lanes >= WB hold 0
+    uint64_t excl = 0;
+    if (t < a.nranges)
+      {
+      excl = lookback_exclusive(a.desc, t, agg);
+      // next tile's compressed bytes -> L2
+      const uint8_t* p0 = a.payload + excl;
+      for (uint32_t o = lane * 128u; o < agg; o += 32u * 128u)
+        if (excl + o < a.payload_bytes) asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + o));
+      }
+    if (lane < WB) sh_sz[slot][lane] = mysz;
+    if (lane == 0) { sh_tile[slot] = t; sh_base[slot] = excl; }
+    };
+
+  long long t_ph = a.dbg ? clock64() : 0;
+  if (warp == 0) fetch_tile(0);
+  int cur = 0;
   for (;;)
     {
     __syncthreads();
-    if (threadIdx.x == 0) sh_tile = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = sh_tile;
+    const uint32_t tile = sh_tile[cur];
     if (tile >= a.nranges) break;
+    TB200_PH(0);                                     // (ticket, sizes and look-back were fetched during the previous tile)
     const uint64_t lo = (uint64_t)tile << a.log2B;
     const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
 
     uint32_t szs[WB];
     uint32_t agg = 0;
 #pragma unroll
-    for (int w = 0; w < WB; ++w)
-      {
-      const uint8_t* sz = a.sizes + 2 * ((uint64_t)tile * WB + w);
-      szs[w] = (uint32_t)sz[0] | ((uint32_t)sz[1] << 8);
-      agg += szs[w];
-      }
-    if (warp == 0)
-      {
-      const uint64_t excl = lookback_exclusive(a.desc, tile, agg);
-      if (lane == 0) sh_base = excl;
-      }
-    __syncthreads();
-    const uint64_t base = sh_base;
+    for (int w = 0; w < WB; ++w) { szs[w] = sh_sz[cur][w]; agg += szs[w]; }
+    TB200_PH(1);
+    const uint64_t base = sh_base[cur];
     const bool in_range = base + agg <= a.payload_bytes;
 
     // 1. stage: block w goes to the tail of plane buffer w, at an offset congruent to its global
@@ -888,17 +1058,19 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
           const uint8_t* src = a.payload + off;
           const uint32_t al = (uint32_t)reinterpret_cast<uintptr_t>(src) & 15u;
           const uint32_t d0 = ((pstride - 32u - sz - al) & ~15u) + al;           // block occupies [d0, d0 + sz)
-          uint8_t* dst = planes + (size_t)w * pstride + d0;
-          uint32_t head = (16u - al) & 15u; if (head > sz) head = sz;
-          const uint32_t nv = (sz - head) >> 4;
-          if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+          // whole 16-byte vectors from the boundary below the block to the boundary above it: the few
+          // bytes copied in front of / behind the block land on free buffer space; nothing at or past
+          // the end of the payload is read (src-size operand)
+          const uint8_t* src16 = src - al;
+          const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(planes + (size_t)w * pstride + (d0 - al));
+          const uint32_t nv = (al + sz + 15u) >> 4;
+          const uint64_t left = a.payload_bytes - off + al;            // bytes from src16 to the end of the payload
           for (uint32_t i = threadIdx.x; i < nv; i += WB * 32)
             {
-            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst + head + 16u * i);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(src + head + 16u * i) : "memory");
+            const uint64_t rem = left - 16ull * i;
+            const uint32_t ssz = rem >= 16 ? 16u : (uint32_t)rem;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst_s + 16u * i), "l"(src16 + 16u * i), "r"(ssz) : "memory");
             }
-          const uint32_t done = head + (nv << 4);
-          if (done + threadIdx.x < sz) dst[done + threadIdx.x] = src[done + threadIdx.x];
           if (w == (int)warp) { my_ip = d0; my_end = d0 + sz; }
           }
         off += sz;
@@ -907,12 +1079,16 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    TB200_PH(2);                                     // staging
 
     // 2. decode in place
     uint32_t got = 0xffffffffu;
-    if (sizes_ok) got = lz4_decode_inplace(planes + (size_t)warp * pstride, my_ip, my_end, cnt);
+    if (sizes_ok) got = lz4_decode_inplace(planes + (size_t)warp * pstride, my_ip, my_end, cnt, (a.dbg && warp == 1) ? a.dbg + 24 : nullptr);
     if (got != cnt && lane == 0) *a.status = 1;
+    TB200_PH(3);                                     // decode of this warp's plane
+    if (warp == 0) fetch_tile(cur ^ 1);
     __syncthreads();
+    TB200_PH(4);                                     // wait for the slowest plane
 
     // 3. merge: element i = bytes planes[p][i], p = 0..WB-1 (LSB first)
     uint8_t* gout = reinterpret_cast<uint8_t*>(a.out) + lo * WB;
@@ -932,6 +1108,7 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
       constexpr int EPV = 16 / WB;
       const uint32_t nvec = cnt / EPV;
       uint4* g4 = reinterpret_cast<uint4*>(gout);
+#pragma unroll 4
       for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x)
         {
         uint32_t w[4] = {0, 0, 0, 0};
@@ -963,7 +1140,7 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
           w[0] = __byte_perm(a01, a23, 0x5410); w[1] = __byte_perm(a45, a67, 0x5410);
           w[2] = __byte_perm(a01, a23, 0x7632); w[3] = __byte_perm(a45, a67, 0x7632);
           }
-        g4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        __stcs(g4 + i, make_uint4(w[0], w[1], w[2], w[3]));
         }
       for (uint32_t i = nvec * EPV + threadIdx.x; i < cnt; i += blockDim.x)
         for (int p = 0; p < WB; ++p) gout[(size_t)i * WB + p] = planes[p * pstride + i];
@@ -973,6 +1150,8 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
       for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
         for (int p = 0; p < WB; ++p) gout[(size_t)i * WB + p] = planes[p * pstride + i];
       }
+    TB200_PH(5);                                     // merge
+    cur ^= 1;
     }
   }
 
