@@ -445,48 +445,43 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
       const uint32_t nvec = cnt / EPV;
       const uint4* g4 = reinterpret_cast<const uint4*>(gin);
       const uint32_t nfull = nvec / (32 * UN);                       // whole batches of UN vectors per lane
-      uint4 cur[UN], nxt[UN];
+      const uint32_t sel2 = p | ((2u + p) << 4) | ((4u + p) << 8) | ((6u + p) << 12);
+      auto put = [&](const uint4 v, uint32_t i)
+        { // byte p of every element of vector i -> plane buffer
+        if (WB == 1) reinterpret_cast<uint4*>(buf)[i] = v;
+        else if (WB == 4) reinterpret_cast<uint32_t*>(buf)[i] = plane_bytes<4>(v, p);
+        else if (WB == 2) reinterpret_cast<uint2*>(buf)[i] = make_uint2(__byte_perm(v.x, v.y, sel2), __byte_perm(v.z, v.w, sel2));
+        else reinterpret_cast<uint16_t*>(buf)[i] = (uint16_t)plane_bytes<8>(v, p);
+        };
+      // two register sets used alternately (no copies between them): while one batch is split,
+      // the loads of the next one are in flight
+      uint4 ra[UN], rb[UN];
       if (nfull)
         {
 #pragma unroll
-        for (int u = 0; u < UN; ++u) cur[u] = __ldg(g4 + lane + 32 * u);
+        for (int u = 0; u < UN; ++u) ra[u] = __ldg(g4 + lane + 32 * u);
         }
-      for (uint32_t bidx = 0; bidx < nfull; ++bidx)
+      uint32_t bidx = 0;
+      while (bidx < nfull)
         {
         if (bidx + 1 < nfull)
           {
 #pragma unroll
-          for (int u = 0; u < UN; ++u) nxt[u] = __ldg(g4 + (bidx + 1) * 32 * UN + lane + 32 * u);
+          for (int u = 0; u < UN; ++u) rb[u] = __ldg(g4 + (bidx + 1) * 32 * UN + lane + 32 * u);
           }
 #pragma unroll
-        for (int u = 0; u < UN; ++u)
+        for (int u = 0; u < UN; ++u) put(ra[u], bidx * 32 * UN + lane + 32 * u);
+        if (++bidx >= nfull) break;
+        if (bidx + 1 < nfull)
           {
-          const uint32_t i = bidx * 32 * UN + lane + 32 * u;
-          const uint4 v = cur[u];
-          if (WB == 1) reinterpret_cast<uint4*>(buf)[i] = v;
-          else if (WB == 4) reinterpret_cast<uint32_t*>(buf)[i] = plane_bytes<4>(v, p);
-          else if (WB == 2)
-            {
-            const uint32_t sel = p | ((2u + p) << 4) | ((4u + p) << 8) | ((6u + p) << 12);
-            reinterpret_cast<uint2*>(buf)[i] = make_uint2(__byte_perm(v.x, v.y, sel), __byte_perm(v.z, v.w, sel));
-            }
-          else reinterpret_cast<uint16_t*>(buf)[i] = (uint16_t)plane_bytes<8>(v, p);
+#pragma unroll
+          for (int u = 0; u < UN; ++u) ra[u] = __ldg(g4 + (bidx + 1) * 32 * UN + lane + 32 * u);
           }
 #pragma unroll
-        for (int u = 0; u < UN; ++u) cur[u] = nxt[u];
+        for (int u = 0; u < UN; ++u) put(rb[u], bidx * 32 * UN + lane + 32 * u);
+        ++bidx;
         }
-      for (uint32_t i = nfull * 32 * UN + lane; i < nvec; i += 32)
-        {
-        const uint4 v = __ldg(g4 + i);
-        if (WB == 1) reinterpret_cast<uint4*>(buf)[i] = v;
-        else if (WB == 4) reinterpret_cast<uint32_t*>(buf)[i] = plane_bytes<4>(v, p);
-        else if (WB == 2)
-          {
-          const uint32_t sel = p | ((2u + p) << 4) | ((4u + p) << 8) | ((6u + p) << 12);
-          reinterpret_cast<uint2*>(buf)[i] = make_uint2(__byte_perm(v.x, v.y, sel), __byte_perm(v.z, v.w, sel));
-          }
-        else reinterpret_cast<uint16_t*>(buf)[i] = (uint16_t)plane_bytes<8>(v, p);
-        }
+      for (uint32_t i = nfull * 32 * UN + lane; i < nvec; i += 32) put(__ldg(g4 + i), i);
       for (uint32_t i = nvec * EPV + lane; i < cnt; i += 32) buf[i] = gin[(size_t)i * WB + p];
       }
     else
@@ -735,17 +730,25 @@ __device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint3
       uint32_t xa = (opm + 64u) & ~15u;                                  // aligned, inside the table: rewriting [xa, opm+64) is harmless
       const uint32_t nv = (end - xa) >> 4;
       const uint32_t t0 = xa - opm;
-      constexpr int UN = 4;
-      for (uint32_t i0 = 0; i0 < nv; i0 += 32 * UN)
+      if (nv <= 64u)
+        { // up to 1 KiB: one or two vectors per lane, nothing computed that is not stored
+        if (lane < nv) *reinterpret_cast<uint4*>(buf + xa + 16u * lane) = smem_read128(buf, opm + modo(t0 + 16u * lane));
+        if (lane + 32u < nv) *reinterpret_cast<uint4*>(buf + xa + 16u * (lane + 32u)) = smem_read128(buf, opm + modo(t0 + 16u * (lane + 32u)));
+        }
+      else
         {
-        uint4 v[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) v[u] = smem_read128(buf, opm + modo(t0 + 16u * (i0 + lane + 32 * u)));
-#pragma unroll
-        for (int u = 0; u < UN; ++u)
+        constexpr int UN = 4;
+        for (uint32_t i0 = 0; i0 < nv; i0 += 32 * UN)
           {
-          const uint32_t i = i0 + lane + 32 * u;
-          if (i < nv) *reinterpret_cast<uint4*>(buf + xa + 16u * i) = v[u];
+          uint4 v[UN];
+#pragma unroll
+          for (int u = 0; u < UN; ++u) v[u] = smem_read128(buf, opm + modo(t0 + 16u * (i0 + lane + 32 * u)));
+#pragma unroll
+          for (int u = 0; u < UN; ++u)
+            {
+            const uint32_t i = i0 + lane + 32 * u;
+            if (i < nv) *reinterpret_cast<uint4*>(buf + xa + 16u * i) = v[u];
+            }
           }
         }
       const uint32_t done = xa + (nv << 4);
@@ -769,187 +772,69 @@ __device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint3
   }
 
 // Decodes the block buf[ip, iend) into buf[0, cap).  Returns the bytes produced or 0xffffffff.
-//
-// A block is a chain of sequences whose positions are only known by walking the tokens, but the
-// walk itself touches nothing but a few length bytes.  So the decoder works in batches of up to
-// 32 sequences:
-//   1. PARSE   the warp walks the tokens; lane s keeps the descriptor of sequence s of the batch
-//              (literal source and length, output position, offset, match length)
-//   2. LITERALS of all sequences of the batch at once: lane s copies its own short run byte by
-//              byte (runs never overlap each other's sources); long runs move warp-wide
-//   3. MATCHES in order.  Up to four at a time, eight lanes each, when they cannot see each
-//              other's output (source inside the sequence's own literals or below the first match
-//              of the group); otherwise one at a time with the whole warp.
-// Output never passes the unread input (LZ4's in-place margin), so deferring the copies of a
-// batch is safe: everything a batch writes lies below the next batch's first token.
+// One sequence per iteration, every step warp-wide.  A lone warp issues one dependent instruction
+// every ~6 cycles, so the loop is written for instruction count: the token and the 31 bytes behind
+// it arrive in one read, a short sequence takes its literals, offset and length continuation out
+// of that register, and the match generator does no work it does not need.  (A variant that parsed
+// 32 sequences ahead and ran literals / independent matches in lane groups executed more
+// instructions on the critical warp than it saved and was slower on index planes.)
 // The checks are the memory-safety ones (every access stays inside the buffer for any input); a
 // malformed block is reported through the byte count it produces.
-#define LZ4_DEC_T(i) do { if (dbg && lane == 0) { const long long t__ = clock64(); atomicAdd(dbg + (i), (unsigned long long)(t__ - t_dec)); t_dec = t__; } } while (0)
-__device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip, uint32_t iend, uint32_t cap, unsigned long long* dbg = nullptr)
+__device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip, uint32_t iend, uint32_t cap)
   {
   const unsigned lane = lane_id();
   uint32_t op = 0;
   if (ip >= iend) return 0xffffffffu;
-  bool finished = false;
-  long long t_dec = dbg ? clock64() : 0;
-  while (!finished)
+  for (;;)
     {
-    // ---- 1. parse ----
-    LZ4_DEC_T(3);
-    uint32_t d_src = 0, d_lit = 0, d_op = 0, d_off = 1, d_mlen = 0;
-    uint32_t ns = 0;
-    while (ns < 32u)
+    // the token and the 31 bytes behind it in one read (32 readable bytes follow every block)
+    const uint32_t b = buf[ip + lane];
+    const uint32_t token = __shfl_sync(FULL, b, 0);
+    uint32_t lit = token >> 4, ml = token & 15u, offset;
+    if (lit < 15u)
       {
-      if (ip >= iend) return 0xffffffffu;
-      // the token and the 31 bytes behind it in one read (32 readable bytes follow every block)
-      const uint32_t b = buf[ip + lane];
-      const uint32_t token = __shfl_sync(FULL, b, 0);
-      uint32_t lit = token >> 4, ml = token & 15u, offset = 1, src, mlen = 0;
-      bool last;
-      if (lit < 15u)
-        {
-        const uint32_t e = lit + 1u;                                // index of the offset's low byte inside b
-        src = ip + 1u;
-        ip += e;
-        last = ip >= iend;
-        if (!last)
-          {
-          offset = __shfl_sync(FULL, b, e) | (__shfl_sync(FULL, b, e + 1u) << 8);
-          ip += 2;
-          if (ml == 15u)
-            { // continuation bytes start at index e+2 of b
-            const unsigned m = __ballot_sync(FULL, b != 255u) >> (e + 2u);
-            if (m)
-              {
-              const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
-              ml += 255u * k + __shfl_sync(FULL, b, e + 2u + k);
-              ip += k + 1u;
-              }
-            else
-              {
-              ml += 255u * (30u - e); ip += 30u - e;
-              ml += lz4_read_ext(buf, ip, iend);
-              }
-            }
-          }
-        }
-      else
-        {
-        ip += 1;
-        lit += lz4_read_ext(buf, ip, iend);
-        src = ip;
-        if (lit > iend || ip + lit > iend) return 0xffffffffu;
-        ip += lit;
-        last = ip >= iend;
-        if (!last)
-          {
-          offset = (uint32_t)buf[ip] | ((uint32_t)buf[ip + 1] << 8);
-          ip += 2;
-          if (ml == 15u) ml += lz4_read_ext(buf, ip, iend);
-          }
-        }
-      if (!last) mlen = ml + LZ4_MINMATCH;
-      // literals copy forward in place (dst <= src); everything stays inside [0, cap) and [.., iend]
-      if (ip > iend || mlen > cap || lit > cap || op + lit + mlen > cap || op > src || (!last && (offset == 0 || offset > op + lit))) return 0xffffffffu;
-      if (lane == ns) { d_src = src; d_lit = lit; d_op = op; d_off = offset; d_mlen = mlen; }
-      op += lit + mlen;
-      ++ns;
-      if (last) { finished = true; break; }
-      }
-
-    LZ4_DEC_T(0);
-    // ---- 2. literals ----
-    // A later run's destination may overlap an earlier run's source (output trails the input by
-    // less than a sequence where the data compresses poorly), so nothing is written before every
-    // source has been read: short runs (<= 16 bytes) are fetched into registers by all lanes at
-    // once, long runs then move one after the other in stream order with the whole warp, and the
-    // short runs are stored last.
-    const bool mine = lane < ns;
-      {
-      const bool shortrun = mine && d_lit <= 16u;
-      uint4 lv = make_uint4(0, 0, 0, 0);
-      if (shortrun && d_lit) lv = smem_read128(buf, d_src);
+      const uint32_t e = lit + 1u;                                  // index of the offset's low byte inside b
+      if (ip + e > iend || op + lit > cap) return 0xffffffffu;
       __syncwarp();
-      unsigned longs = __ballot_sync(FULL, mine && d_lit > 16u);
-      while (longs)
-        {
-        const int sq = __ffs((int)longs) - 1;
-        longs &= longs - 1u;
-        lz4_smem_move<true>(buf, __shfl_sync(FULL, d_op, sq), __shfl_sync(FULL, d_src, sq), __shfl_sync(FULL, d_lit, sq));
-        __syncwarp();
-        }
-      if (shortrun)
-        {
-        const uint32_t w[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-        for (uint32_t j = 0; j < 16; ++j)
-          if (j < d_lit) buf[d_op + j] = (uint8_t)(w[j >> 2] >> (8u * (j & 3u)));
+      if (lane - 1u < lit) buf[op + lane - 1u] = (uint8_t)b;        // lanes 1..lit
+      op += lit; ip += e;
+      if (ip >= iend) break;                                        // last sequence has no match part
+      offset = __shfl_sync(FULL, b, e) | (__shfl_sync(FULL, b, e + 1u) << 8);
+      ip += 2;
+      if (ml == 15u)
+        { // continuation bytes start at index e+2 of b
+        const unsigned m = __ballot_sync(FULL, b != 255u) >> (e + 2u);
+        if (m)
+          {
+          const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+          ml += 255u * k + __shfl_sync(FULL, b, e + 2u + k);
+          ip += k + 1u;
+          }
+        else
+          {
+          ml += 255u * (30u - e); ip += 30u - e;
+          ml += lz4_read_ext(buf, ip, iend);
+          }
         }
       }
-    __syncwarp();
-    LZ4_DEC_T(1);
-
-    // ---- 3. matches ----
-    const uint32_t nm = finished ? ns - 1u : ns;                      // the block's last sequence has no match
-    const uint32_t grp = lane >> 3, li = lane & 7u;
-    uint32_t s0 = 0;
-    while (s0 < nm)
+    else
       {
-      // candidate group: sequences s0 .. s0+3, eight lanes each
-      const uint32_t q = s0 + grp;
-      const uint32_t g_lit = __shfl_sync(FULL, d_lit, q & 31u), g_off = __shfl_sync(FULL, d_off, q & 31u);
-      const uint32_t g_mlen = __shfl_sync(FULL, d_mlen, q & 31u);
-      const uint32_t g_opm = __shfl_sync(FULL, d_op, q & 31u) + g_lit;
-      const uint32_t first_opm = __shfl_sync(FULL, g_opm, 0);
-      const bool is_lut = g_off <= 32u && g_mlen > g_off;
-      const bool is_small_move = g_off >= g_mlen && g_mlen <= 128u;
-      const uint32_t need = g_off < g_mlen ? g_off : g_mlen;          // source bytes that must already exist
-      const bool indep = grp == 0 || g_off <= g_lit || g_opm - g_off + need <= first_opm;
-      const bool can = q < nm && g_mlen <= 2048u && (is_lut || is_small_move) && indep;
-      const unsigned canmask = __ballot_sync(FULL, can);
-      // number of leading groups that can run together
-      const uint32_t together = (canmask & 1u) == 0 ? 0u : (canmask & 0x100u) == 0 ? 1u : (canmask & 0x10000u) == 0 ? 2u : (canmask & 0x1000000u) == 0 ? 3u : 4u;
-      if (together >= 2u)
-        {
-        const bool on = grp < together;
-        const uint32_t inv = c_lz4_inv[on && is_lut ? g_off : 2u];
-        const uint32_t keep = g_off == 1u ? 0u : 0xffffffffu;
-        auto modo = [&](uint32_t t) { return (t - g_off * __umulhi(t, inv)) & keep; };
-        if (on && !is_lut)
-          for (uint32_t t = li; t < g_mlen; t += 8) buf[g_opm + t] = buf[g_opm - g_off + t];
-        if (on && is_lut)
-          {
-          const uint8_t* ms = buf + g_opm - g_off;
-          uint32_t pat[8];
-#pragma unroll
-          for (uint32_t j = 0; j < 8; ++j) pat[j] = ms[modo(8u * li + j)];
-#pragma unroll
-          for (uint32_t j = 0; j < 8; ++j) if (8u * li + j < g_mlen) buf[g_opm + 8u * li + j] = (uint8_t)pat[j];
-          }
-        __syncwarp();
-        if (on && is_lut && g_mlen > 64u)
-          {
-          const uint32_t end = g_opm + g_mlen;
-          const uint32_t xa = (g_opm + 64u) & ~15u;
-          const uint32_t nv = (end - xa) >> 4;
-          const uint32_t t0 = xa - g_opm;
-          for (uint32_t i = li; i < nv; i += 8)
-            *reinterpret_cast<uint4*>(buf + xa + 16u * i) = smem_read128(buf, g_opm + modo(t0 + 16u * i));
-          const uint32_t done = xa + (nv << 4);
-          for (uint32_t t = done + li; t < end; t += 8) buf[t] = buf[g_opm + modo(t - g_opm)];
-          }
-        __syncwarp();
-        s0 += together;
-        }
-      else
-        {
-        const uint32_t w_lit = __shfl_sync(FULL, d_lit, s0 & 31u);
-        lz4_match_warp(buf, __shfl_sync(FULL, d_op, s0 & 31u) + w_lit, __shfl_sync(FULL, d_off, s0 & 31u), __shfl_sync(FULL, d_mlen, s0 & 31u));
-        __syncwarp();
-        s0 += 1;
-        }
+      ip += 1;
+      lit += lz4_read_ext(buf, ip, iend);
+      if (lit > iend || ip + lit > iend || op + lit > cap || op > ip) return 0xffffffffu;
+      lz4_smem_move<true>(buf, op, ip, lit);
+      ip += lit; op += lit;
+      if (ip >= iend) break;
+      offset = (uint32_t)buf[ip] | ((uint32_t)buf[ip + 1] << 8);
+      ip += 2;
+      if (ml == 15u) ml += lz4_read_ext(buf, ip, iend);
       }
-    LZ4_DEC_T(2);
+    const uint32_t mlen = ml + LZ4_MINMATCH;
+    if (ip > iend || mlen > cap || offset == 0 || offset > op || op + mlen > cap) return 0xffffffffu;
+    __syncwarp();                                   // literals of this sequence are visible
+    lz4_match_warp(buf, op, offset, mlen);
+    op += mlen;
+    __syncwarp();
     }
   return op;
   }
@@ -1083,7 +968,7 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
 
     // 2. decode in place
     uint32_t got = 0xffffffffu;
-    if (sizes_ok) got = lz4_decode_inplace(planes + (size_t)warp * pstride, my_ip, my_end, cnt, (a.dbg && warp == 1) ? a.dbg + 24 : nullptr);
+    if (sizes_ok) got = lz4_decode_inplace(planes + (size_t)warp * pstride, my_ip, my_end, cnt);
     if (got != cnt && lane == 0) *a.status = 1;
     TB200_PH(3);                                     // decode of this warp's plane
     if (warp == 0) fetch_tile(cur ^ 1);
