@@ -242,6 +242,60 @@ def test_archive_roundtrip_all_types(ours, oracle, golden):
         assert cnt == wcnt and arr.tobytes() == want.tobytes(), ty
 
 
+def test_pipelined_archive_is_byte_identical(ours, oracle, monkeypatch):
+    """host-resident streams larger than a few slabs go through the H2D / kernel / D2H slab pipeline:
+    the archive must be byte-identical to the one-shot path and decode through both readers"""
+    from trico_b200.synth import grid_mesh
+    v, t = grid_mesh(900, 700, jitter=1.0, seed=5)              # 7.5 MB of vertices, 15 MB of indices
+    nv, nt = v.shape[0], t.shape[0]
+    rng = np.random.default_rng(3)
+    attr16 = rng.integers(0, 5000, nv * 3, dtype=np.uint16)
+    attr64 = (np.arange(nv * 2, dtype=np.uint64) << np.uint64(7)) ^ rng.integers(0, 100, nv * 2).astype(np.uint64)
+    vd = v.astype(np.float64)
+    streams = [(1, v, nv), (3, t, nt), (2, vd, nv), (18, attr16, attr16.size), (20, attr64, attr64.size)]
+    monkeypatch.setenv("TRICO_B200_NO_PIPELINE", "1")
+    one_shot = ours.encode(streams)
+    monkeypatch.delenv("TRICO_B200_NO_PIPELINE")
+    monkeypatch.setenv("TRICO_B200_SLAB_MB", "1")
+    piped = ours.encode(streams)
+    assert piped == one_shot
+    version, dec = ours.decode(piped, oracle)                      # pipelined reader
+    monkeypatch.setenv("TRICO_B200_NO_PIPELINE", "1")
+    version2, dec2 = ours.decode(piped, oracle)                    # one-shot reader
+    _, dec3 = oracle.read_archive(piped)                           # CPU oracle
+    for (ty, data, cnt), a, b, c in zip(streams, dec, dec2, dec3):
+        want = np.ascontiguousarray(data).reshape(-1).tobytes()
+        assert a[2].tobytes() == want and b[2].tobytes() == want and c[2].tobytes() == want, ty
+
+
+def test_batch_of_mixed_meshes(ours, oracle):
+    """C3/C4/C5-shaped inputs at small scale: double positions + double normals + uv + uint64 indices,
+    a coloured float point cloud, and meshes with float / uint8 / uint16 / uint64 attribute lists;
+    every archive must be readable by the CPU oracle and by our reader, bit-exactly"""
+    from trico_b200.synth import grid_mesh
+    rng = np.random.default_rng(17)
+    for m in range(12):
+        side = 8 + 5 * m
+        v, t = grid_mesh(side, side + 1, jitter=1.0, seed=m)
+        nv, nt = v.shape[0], t.shape[0]
+        vd = v.astype(np.float64)
+        nrm = rng.standard_normal((nv, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        uv = np.stack([np.arange(nv) % side / (side - 1), np.arange(nv) // side / side], axis=1)
+        col = (128 + 100 * np.sin(0.5 * v[:, 0])).astype(np.uint32) | (np.uint32(255) << np.uint32(24))
+        streams = [(2, vd, nv), (10, nrm, nv), (6, uv, nv), (4, t.astype(np.uint64), nt),          # C3
+                   (1, v, nv), (13, col, nv),                                                        # C4
+                   (15, (0.1 * v[:, 2]).astype(np.float32), nv), (17, (np.arange(nv) >> 4).astype(np.uint8), nv),
+                   (18, (v[:, 2] * 100).astype(np.int32).astype(np.uint16), nv),
+                   (20, (np.uint64(m) << np.uint64(32)) | np.arange(nv, dtype=np.uint64), nv)]     # C5
+        blob = ours.encode(streams)
+        _, dec = oracle.read_archive(blob)
+        _, mine = ours.decode(blob, oracle)
+        for (ty, data, cnt), a, b in zip(streams, dec, mine):
+            want = np.ascontiguousarray(data).reshape(-1).tobytes()
+            assert a[0] == ty and a[2].tobytes() == want, (m, ty, "oracle")
+            assert b[0] == ty and b[2].tobytes() == want, (m, ty, "ours")
+
+
 def test_empty_archive_and_errors(ours):
     L = ours.lib
     a = L.trico_open_archive_for_writing(1024)

@@ -379,7 +379,7 @@ static int use_pipeline(const slab_plan* p, uint64_t raw_bytes)
   {
   const char* s = getenv("TRICO_B200_NO_PIPELINE");
   if (s && s[0] == '1') return 0;
-  return p->nslabs >= 3 && raw_bytes >= (8u << 20);
+  return p->nslabs >= 3 && raw_bytes >= (1u << 20);
   }
 
 static int write_stream_pipelined(archive* a, int type, const uint8_t* data, uint32_t count, const slab_plan* p)
