@@ -190,15 +190,31 @@ extern "C" uint64_t tb200_v1_stream_bound(int type, uint32_t count, int log2_chu
 // ------------------------------------------------------------------------------------------------
 // chunked FPC
 // ------------------------------------------------------------------------------------------------
-template <typename W, int NCOMP>
-static int launch_fpc_encode(tb200_ctx* c, const FpcEncodeArgs& a)
+template <typename W, int NCOMP, int R, int SB>
+static int launch_fpc_encode_lanes(tb200_ctx* c, FpcEncodeArgs a)
   {
+  using WIN = FpcWindow<W, SB>;
+  constexpr int NWARPS = NCOMP * R;
   const uint32_t S = 1u << a.log2S;
-  const uint32_t slot = (fpc_chunk_bound(S, sizeof(W)) + 15u + 16u) & ~15u;
-  const size_t smem = (size_t)FPC_ENC_WARPS * S * sizeof(W) + (size_t)FPC_ENC_WARPS * slot +
-                      (size_t)FPC_ENC_WARPS * ((1u << a.e1) + (1u << a.e2)) * sizeof(W);
-  if (!set_smem(fpc_encode_kernel<W, NCOMP>, smem, c)) return 0;
-  fpc_encode_kernel<W, NCOMP><<<a.ntiles, FPC_ENC_WARPS * 32, smem, c->stream>>>(a);
+  a.ntiles = (a.nranges + 32 * R - 1) / (32 * R);
+  if (!ws_prepare(c, a.ntiles + 1, &a.ticket, &a.desc)) return 0;
+  if (!a.total_field) a.total_field = reinterpret_cast<uint8_t*>(a.desc + a.ntiles);
+  const size_t smem = (size_t)NWARPS * 32 * WIN::VECS * 16 +
+                      (size_t)32 * R * (SB * NCOMP * (sizeof(W) / 4) + 4) * 4 +
+                      (size_t)NWARPS * 32 * ((1u << a.e1) + (1u << a.e2)) * sizeof(W);
+  if (!set_smem(fpc_encode_lanes_kernel<W, NCOMP, R, SB>, smem, c)) return 0;
+  int per_sm = 0, sms = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc_encode_lanes_kernel<W, NCOMP, R, SB>, NWARPS * 32, smem));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  if (per_sm < 1) return fail_msg("fpc_encode_lanes_kernel does not fit on an SM");
+  // persistent grid, every CTA resident (the look-back relies on it); a CTA reuses its scratch slots
+  uint32_t grid = (uint32_t)per_sm * (uint32_t)sms;
+  if (grid > a.ntiles) grid = a.ntiles;
+  a.slot = (fpc_chunk_bound(S, sizeof(W)) + 16u + 15u) & ~15u;
+  uint8_t* scratch = nullptr;
+  if (!big_prepare(c, (size_t)grid * NWARPS * 32 * a.slot + 64, &scratch)) return 0;
+  a.scratch = scratch;
+  fpc_encode_lanes_kernel<W, NCOMP, R, SB><<<grid, NWARPS * 32, smem, c->stream>>>(a);
   c->launches++;
   CK(cudaGetLastError());
   return 1;
@@ -214,21 +230,17 @@ extern "C" int tb200_fpc_encode(tb200_ctx* c, int wordsize, int ncomp, const voi
   FpcEncodeArgs a;
   a.in = d_in; a.n = n; a.log2S = log2_chunk; a.e1 = e1; a.e2 = e2;
   a.nranges = (uint32_t)((n + ((uint64_t)1 << log2_chunk) - 1) >> log2_chunk);
-  const uint32_t KT = FPC_ENC_WARPS / ncomp;
-  a.ntiles = (a.nranges + KT - 1) / KT;
-  a.sizes = d_sizes; a.payload = d_payload; a.total = d_total;
-  if (a.ntiles == 0)
+  a.ntiles = 0; a.ticket = nullptr; a.desc = nullptr; a.scratch = nullptr; a.slot = 0;
+  a.sizes = d_sizes; a.payload = d_payload; a.total = d_total; a.total_field = d_total_field;
+  if (a.nranges == 0)
     {
     CK(cudaMemsetAsync(d_total, 0, 8, c->stream));
     if (d_total_field) CK(cudaMemsetAsync(d_total_field, 0, 8, c->stream));
     return 1;
     }
-  if (!ws_prepare(c, a.ntiles + 1, &a.ticket, &a.desc)) return 0;
-  // when the caller does not want the unaligned header copy, point it at scratch
-  a.total_field = d_total_field ? d_total_field : reinterpret_cast<uint8_t*>(a.desc + a.ntiles);
   if (wordsize == 4)
-    return ncomp == 3 ? launch_fpc_encode<uint32_t, 3>(c, a) : ncomp == 2 ? launch_fpc_encode<uint32_t, 2>(c, a) : launch_fpc_encode<uint32_t, 1>(c, a);
-  return ncomp == 3 ? launch_fpc_encode<uint64_t, 3>(c, a) : ncomp == 2 ? launch_fpc_encode<uint64_t, 2>(c, a) : launch_fpc_encode<uint64_t, 1>(c, a);
+    return ncomp == 3 ? launch_fpc_encode_lanes<uint32_t, 3, 1, 32>(c, a) : ncomp == 2 ? launch_fpc_encode_lanes<uint32_t, 2, 2, 32>(c, a) : launch_fpc_encode_lanes<uint32_t, 1, 4, 32>(c, a);
+  return ncomp == 3 ? launch_fpc_encode_lanes<uint64_t, 3, 1, 16>(c, a) : ncomp == 2 ? launch_fpc_encode_lanes<uint64_t, 2, 2, 16>(c, a) : launch_fpc_encode_lanes<uint64_t, 1, 4, 16>(c, a);
   }
 
 template <typename W, int NCOMP, int R, int SB>

@@ -211,6 +211,8 @@ struct FpcEncodeArgs
   uint64_t* total;         // aligned device scalar with the same value
   uint64_t* desc;          // look-back descriptors [ntiles], zeroed
   uint32_t* ticket;        // zeroed
+  uint8_t* scratch;        // lane-per-chunk kernel: one slot per chunk in flight (grid * chunks per tile)
+  uint32_t slot;           // bytes per scratch slot (multiple of 16, >= chunk bound + 16)
   };
 
 constexpr int FPC_ENC_WARPS = 12;
@@ -622,6 +624,318 @@ fpc_decode_kernel(const FpcDecodeArgs a)
         }
       }
     __syncthreads();
+    }
+  }
+
+// ---------------------------------------------------------------------------------------------
+// K3: chunked encode, LANE PER CHUNK - the mirror image of K4.
+//
+// The warp-cooperative routine above (32 consecutive values per warp step) spends most of its
+// ~180 instructions per step on cross-lane bookkeeping (match.any, shuffles, ballots, scattered byte
+// stores).  Chunks are independent, so the cheaper way to use a warp is the decoder's: every lane
+// runs the plain serial predictor of the reference on its own chunk (tables lane-interleaved in
+// shared memory), and the memory system is served by the warp as a whole:
+//   a. the CTA stages a slab of SB values of all its ranges with 16-byte cp.async copies
+//      (this is trico_transpose_*_aos_to_soa, transpose_aos_to_soa.c:8-82, fused)
+//   b. every lane encodes SB values of its chunk into a byte window in shared memory (32-bit
+//      accumulator, one word store per four output bytes)
+//   c. the warp writes the completed 16-byte vectors of its 32 windows to the chunks' scratch
+//      slots in global memory (the CTA reuses its slots tile after tile, so they live in L2)
+//   d. at the end of the tile: chunk sizes -> block scan -> decoupled look-back -> every chunk is
+//      copied once from its slot to its final offset; the u16 size table and the stream's
+//      payload_bytes field are written by the same kernel.
+// CTA = NCOMP * R warps; warp w owns component w % NCOMP of 32 consecutive ranges (lane = range).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fpc_emit(uint32_t* wrow, uint32_t& acc, uint32_t& fill, uint32_t& wp, uint32_t le, uint32_t n)
+  { // appends n (0..4) bytes; `le` holds them in memory order in its low bytes, upper bytes zero
+  const uint32_t lo = acc | (le << (8u * fill));
+  const uint32_t nf = fill + n;
+  if (nf >= 4u) { wrow[wp++] = lo; acc = __funnelshift_rc(le, 0u, 32u - 8u * fill); fill = nf - 4u; }
+  else { acc = lo; fill = nf; }
+  }
+
+// warp copy of n bytes between global buffers; src 16-byte aligned (read around L1), dst arbitrary
+__device__ __forceinline__ void warp_copy_global(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n)
+  {
+  const unsigned lane = lane_id();
+  uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+  if (head > n) head = n;
+  if (lane < head) dst[lane] = __ldcg(src + lane);
+  const uint32_t nvec = (n - head) >> 4;
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src + (head & ~3u));
+  const unsigned sh = (head & 3u) * 8u;
+  uint4* dv = reinterpret_cast<uint4*>(dst + head);
+  constexpr int UN = 2;
+  for (uint32_t i0 = 0; i0 < nvec; i0 += 32 * UN)
+    {
+    uint32_t w[UN][5];
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      {
+      const uint32_t i = i0 + lane + 32 * u;
+      if (i < nvec)
+        {
+        const uint32_t* q = sw + 4 * i;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) w[u][j] = __ldcg(q + j);
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      {
+      const uint32_t i = i0 + lane + 32 * u;
+      if (i < nvec)
+        dv[i] = make_uint4(__funnelshift_r(w[u][0], w[u][1], sh), __funnelshift_r(w[u][1], w[u][2], sh),
+                           __funnelshift_r(w[u][2], w[u][3], sh), __funnelshift_r(w[u][3], w[u][4], sh));
+      }
+    }
+  const uint32_t done = head + (nvec << 4);
+  if (done + lane < n) dst[done + lane] = __ldcg(src + done + lane);
+  }
+
+template <typename W, int NCOMP, int R, int SB>
+__global__ void __launch_bounds__(NCOMP * R * 32)
+fpc_encode_lanes_kernel(const FpcEncodeArgs a)
+  {
+  using TR = FpcTraits<W>;
+  using WIN = FpcWindow<W, SB>;
+  constexpr int NWARPS = NCOMP * R;
+  constexpr int NTHREADS = NWARPS * 32;                   // == chunks per tile
+  constexpr int WV = WIN::VECS;                           // 16-byte vectors per lane window
+  constexpr int WPV = sizeof(W) / 4;
+  constexpr int ROWV = SB * NCOMP * WPV / 4;
+  constexpr int ROWW = SB * NCOMP * WPV + 4;
+  static_assert((SB * NCOMP * WPV) % 4 == 0, "staged rows must be whole vectors");
+  static_assert(SB % TR::GROUP == 0, "sub-blocks hold whole groups");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t nt1 = 1u << a.e1, nt2 = 1u << a.e2;
+  uint32_t* win = reinterpret_cast<uint32_t*>(smem_raw);                               // [NWARPS][32][WV*4]
+  uint32_t* stagebuf = win + (size_t)NWARPS * 32 * WV * 4;                             // [32*R][ROWW]
+  W* tables = reinterpret_cast<W*>(stagebuf + (size_t)32 * R * ROWW);                  // [NWARPS][nt1+nt2][32]
+  __shared__ uint32_t sh_tile;
+  __shared__ uint32_t sh_size[NTHREADS];                  // stream order: index = range_local * NCOMP + component
+  __shared__ uint32_t sh_off[NTHREADS];
+  __shared__ uint32_t sh_wsum[NWARPS];
+  __shared__ uint64_t sh_base;
+
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t c = warp % NCOMP, rgrp = warp / NCOMP;
+  const uint32_t klocal = rgrp * 32 + lane;
+  const uint32_t S = 1u << a.log2S;
+  const uint32_t h2 = (uint32_t)a.e2 >> 1, m2 = nt2 - 1;
+  W* T1 = tables + (size_t)warp * (nt1 + nt2) * 32 + lane;
+  W* T2 = T1 + (size_t)nt1 * 32;
+  uint32_t* wrow = win + ((size_t)warp * 32 + lane) * WV * 4;
+  const uint4* wwarp4 = reinterpret_cast<const uint4*>(win + (size_t)warp * 32 * WV * 4);
+  const uint32_t* srow = stagebuf + (size_t)klocal * ROWW + c * WPV;
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stagebuf);
+  uint8_t* cta_scr = a.scratch + (size_t)blockIdx.x * NTHREADS * a.slot;
+  uint8_t* my_scr = cta_scr + (size_t)(klocal * NCOMP + c) * a.slot;
+  const uint8_t* gin = reinterpret_cast<const uint8_t*>(a.in);
+  const bool in_aligned = (reinterpret_cast<uintptr_t>(gin) & 15u) == 0;
+
+  for (;;)
+    {
+    __syncthreads();
+    if (threadIdx.x == 0) sh_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sh_tile;
+    if (tile >= a.ntiles) break;
+
+    const uint64_t k = (uint64_t)tile * (32 * R) + klocal;
+    uint32_t cnt = 0;
+    if (k < a.nranges)
+      {
+      const uint64_t lo = k << a.log2S;
+      cnt = (uint32_t)((a.n - lo < S) ? (a.n - lo) : S);
+      }
+    const uint64_t lo0 = ((uint64_t)tile * (32 * R)) << a.log2S;
+    const uint32_t cnt0 = (uint32_t)((a.n - lo0 < S) ? (a.n - lo0) : S);
+    const bool fast_in = ((uint64_t)tile + 1) * (32 * R) < a.nranges && in_aligned;   // every range of the tile is complete
+
+    for (uint32_t i = 0; i < nt1 + nt2; ++i) T1[(size_t)i * 32] = 0;
+    W pred1 = 0, pred2 = 0, last = 0;
+    uint32_t c1 = 0, c2 = 0;
+    uint32_t acc = 0, fill = 0, wp = 0, flushed = 0;
+
+    // a. slab of SB values per range: row r of the staging tile = range tile*32R + r
+    auto stage_in = [&](uint32_t i0)
+      {
+      if (fast_in)
+        {
+        const uint8_t* tin = gin + (lo0 + i0) * (NCOMP * sizeof(W));
+        const uint32_t row_bytes = (uint32_t)(NCOMP * sizeof(W)) << a.log2S;
+        for (uint32_t ci = threadIdx.x; ci < 32u * R * ROWV; ci += NTHREADS)
+          {
+          const uint32_t r = ci / (uint32_t)ROWV, v = ci - r * (uint32_t)ROWV;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(stage_s + (r * ROWW + 4u * v) * 4u), "l"(tin + (size_t)r * row_bytes + 16u * v) : "memory");
+          }
+        }
+      else
+        {
+        for (uint32_t r = warp; r < 32u * R; r += NWARPS)
+          {
+          const uint64_t kr = (uint64_t)tile * (32 * R) + r;
+          if (kr >= a.nranges) break;
+          const uint64_t lo = kr << a.log2S;
+          const uint32_t rc = (uint32_t)((a.n - lo < S) ? (a.n - lo) : S);
+          if (i0 >= rc) continue;
+          const uint32_t nw = ((rc - i0 < (uint32_t)SB) ? rc - i0 : (uint32_t)SB) * NCOMP * WPV;
+          const uint32_t* gi = reinterpret_cast<const uint32_t*>(gin + (lo + i0) * (NCOMP * sizeof(W)));
+          for (uint32_t q = lane; q < nw; q += 32) stagebuf[(size_t)r * ROWW + q] = gi[q];
+          }
+        }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+
+    stage_in(0);
+    for (uint32_t i0 = 0; i0 < cnt0; i0 += SB)
+      {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+
+      // b. encode up to SB values of this lane's chunk
+      const uint32_t todo = (i0 < cnt) ? ((cnt - i0 < (uint32_t)SB) ? cnt - i0 : (uint32_t)SB) : 0;
+#pragma unroll 1
+      for (uint32_t g = 0; g < (uint32_t)SB / TR::GROUP; ++g)
+        {
+        if (g * TR::GROUP >= todo) break;
+        W xs[TR::GROUP];
+        uint32_t nbs[TR::GROUP];
+        uint32_t bc = 0;
+#pragma unroll
+        for (int jj = 0; jj < TR::GROUP; ++jj)
+          {
+          const uint32_t idx = g * TR::GROUP + jj;
+          uint32_t code = 1, nb = 1;                                // pad slot of the last group: code 1 + one zero byte (fpc.c:196-204, :789-794)
+          W x = 0;
+          if (idx < todo)
+            {
+            const W v = *reinterpret_cast<const W*>(srow + (size_t)idx * NCOMP * WPV);
+            const W x1 = v ^ pred1, x2 = v ^ pred2;
+            T1[(size_t)c1 * 32] = v;
+            c1 = (uint32_t)(v >> (TR::BITS - a.e1));
+            pred1 = T1[(size_t)c1 * 32];
+            const W st = v - last;
+            T2[(size_t)c2 * 32] = st;
+            c2 = ((c2 << h2) ^ (uint32_t)(st >> (TR::BITS - a.e2))) & m2;
+            pred2 = v + T2[(size_t)c2 * 32];
+            last = v;
+            // code selection, fpc.c:146-189 / :635-782
+            const int n1 = sig_bytes(x1);
+            int n2 = sig_bytes(x2); if (n2 == 0) n2 = 1;
+            const bool use2 = (n1 >= 2) && (n2 < n1);
+            code = use2 ? TR::BASE2 + n2 : n1;
+            nb = use2 ? n2 : n1;
+            x = use2 ? x2 : x1;
+            }
+          bc |= code << (TR::CBITS * jj);
+          xs[jj] = x; nbs[jj] = nb;
+          }
+        // code word (big-endian), then the residual bytes, most significant first
+        if (TR::HDR == 3) fpc_emit(wrow, acc, fill, wp, __byte_perm(bc, 0u, 0x4012u), 3u);
+        else              fpc_emit(wrow, acc, fill, wp, bc, 1u);
+#pragma unroll
+        for (int jj = 0; jj < TR::GROUP; ++jj)
+          {
+          const uint32_t nb = nbs[jj];
+          if (sizeof(W) == 4)
+            {
+            const uint32_t xl = __funnelshift_lc(0u, (uint32_t)xs[jj], 32u - 8u * nb);     // left-justified, 0 when nb == 0
+            fpc_emit(wrow, acc, fill, wp, __byte_perm(xl, 0u, 0x0123u), nb);
+            }
+          else
+            {
+            const uint64_t xl = nb ? ((uint64_t)xs[jj] << (8u * (8u - nb))) : 0ull;
+            const uint32_t first = __byte_perm((uint32_t)(xl >> 32), 0u, 0x0123u), second = __byte_perm((uint32_t)xl, 0u, 0x0123u);
+            fpc_emit(wrow, acc, fill, wp, first, nb < 4u ? nb : 4u);
+            fpc_emit(wrow, acc, fill, wp, second, nb > 4u ? nb - 4u : 0u);
+            }
+          }
+        }
+      __syncthreads();                               // the staging tile may be overwritten; window words are visible
+      if (i0 + SB < cnt0) stage_in(i0 + SB);         // next slab crosses L2 -> shared memory while the windows drain
+
+      // c. completed vectors of the warp's 32 windows -> the chunks' scratch slots
+      const uint32_t nf = wp >> 2;
+#pragma unroll
+      for (int it = 0; it < WV; ++it)
+        {
+        const uint32_t ci = (uint32_t)it * 32u + lane;
+        const uint32_t L = ci / (uint32_t)WV, v = ci - L * (uint32_t)WV;
+        const uint32_t nfL = __shfl_sync(FULL, nf, L), posL = __shfl_sync(FULL, flushed, L);
+        if (v < nfL)
+          __stcg(reinterpret_cast<uint4*>(cta_scr + (size_t)((rgrp * 32 + L) * NCOMP + c) * a.slot + posL + 16u * v), wwarp4[ci]);
+        }
+      __syncwarp();
+      if (nf)
+        { // keep the incomplete tail vector at the front of the window
+        const uint32_t rem = wp & 3u;
+        uint32_t t0 = 0, t1 = 0, t2 = 0;
+        if (rem > 0) t0 = wrow[4 * nf];
+        if (rem > 1) t1 = wrow[4 * nf + 1];
+        if (rem > 2) t2 = wrow[4 * nf + 2];
+        if (rem > 0) wrow[0] = t0;
+        if (rem > 1) wrow[1] = t1;
+        if (rem > 2) wrow[2] = t2;
+        flushed += 16u * nf; wp = rem;
+        }
+      }
+
+    // d. tail of every chunk, sizes, offsets, assembly
+    uint32_t total = 0;
+    if (cnt)
+      {
+      if (fill) wrow[wp] = acc;
+      const uint32_t tailb = 4u * wp + fill;                          // < 16
+      total = flushed + tailb;
+      if (tailb) __stcg(reinterpret_cast<uint4*>(my_scr + flushed), *reinterpret_cast<const uint4*>(wrow));
+      }
+    sh_size[klocal * NCOMP + c] = total;
+    __syncthreads();
+      {
+      const uint32_t mine = sh_size[threadIdx.x];
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+        {
+        const uint32_t up = __shfl_up_sync(FULL, incl, o);
+        if (lane >= (unsigned)o) incl += up;
+        }
+      if (lane == 31) sh_wsum[warp] = incl;
+      __syncthreads();
+      uint32_t wbase = 0, tsum = 0;
+#pragma unroll
+      for (int w = 0; w < NWARPS; ++w) { const uint32_t t = sh_wsum[w]; if (w < (int)warp) wbase += t; tsum += t; }
+      sh_off[threadIdx.x] = wbase + incl - mine;
+      if (warp == 0)
+        {
+        const uint64_t excl = lookback_exclusive(a.desc, tile, tsum);
+        if (lane == 0)
+          {
+          sh_base = excl;
+          if (tile == a.ntiles - 1)
+            {
+            *a.total = excl + tsum;
+            store_u64_bytes(a.total_field, excl + tsum);
+            }
+          }
+        }
+      // u16 size table, stream order
+      const uint64_t gq = (uint64_t)tile * NTHREADS + threadIdx.x;
+      if (gq < (uint64_t)a.nranges * NCOMP)
+        {
+        uint8_t* sz = a.sizes + 2 * gq;
+        sz[0] = (uint8_t)mine; sz[1] = (uint8_t)(mine >> 8);
+        }
+      }
+    __syncthreads();
+    const uint64_t base = sh_base;
+    for (uint32_t q = warp; q < (uint32_t)NTHREADS; q += NWARPS)
+      {
+      const uint32_t nbytes = sh_size[q];
+      if (nbytes) warp_copy_global(a.payload + base + sh_off[q], cta_scr + (size_t)q * a.slot, nbytes);
+      }
     }
   }
 
