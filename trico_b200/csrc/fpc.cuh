@@ -694,7 +694,7 @@ __device__ __forceinline__ void warp_copy_global(uint8_t* __restrict__ dst, cons
   }
 
 template <typename W, int NCOMP, int R, int SB>
-__global__ void __launch_bounds__(NCOMP * R * 32)
+__global__ void __launch_bounds__(NCOMP * R * 32, 15 / (NCOMP * R))
 fpc_encode_lanes_kernel(const FpcEncodeArgs a)
   {
   using TR = FpcTraits<W>;
@@ -931,11 +931,40 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
       }
     __syncthreads();
     const uint64_t base = sh_base;
-    for (uint32_t q = warp; q < (uint32_t)NTHREADS; q += NWARPS)
-      {
-      const uint32_t nbytes = sh_size[q];
-      if (nbytes) warp_copy_global(a.payload + base + sh_off[q], cta_scr + (size_t)q * a.slot, nbytes);
+    constexpr int BV = 5;                                  // vectors per lane of the bounce path: chunks up to 2560 bytes
+    if (a.slot <= 32u * BV * 16u && a.slot <= 32u * WV * 16u)
+      { // slot -> registers (the next chunk's loads are in flight while this one is written) -> the warp's
+        // window area -> final offset; the shared-memory hop turns the alignment shift into cheap LDS work
+      uint8_t* bounce = reinterpret_cast<uint8_t*>(win + (size_t)warp * 32 * WV * 4);
+      uint4 cur[BV], nxt[BV];
+      auto fetch = [&](uint4 (&r)[BV], uint32_t q)
+        {
+        const uint32_t nv = (sh_size[q] + 15u) >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(cta_scr + (size_t)q * a.slot);
+#pragma unroll
+        for (int u = 0; u < BV; ++u) if (lane + 32u * u < nv) r[u] = __ldcg(s4 + lane + 32 * u);
+        };
+      if (warp < (unsigned)NTHREADS) fetch(cur, warp);
+      for (uint32_t q = warp; q < (uint32_t)NTHREADS; q += NWARPS)
+        {
+        if (q + NWARPS < (uint32_t)NTHREADS) fetch(nxt, q + NWARPS);
+        const uint32_t nbytes = sh_size[q];
+        const uint32_t nv = (nbytes + 15u) >> 4;
+#pragma unroll
+        for (int u = 0; u < BV; ++u) if (lane + 32u * u < nv) reinterpret_cast<uint4*>(bounce)[lane + 32 * u] = cur[u];
+        __syncwarp();
+        if (nbytes) warp_copy_smem_to_global(a.payload + base + sh_off[q], bounce, nbytes);
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < BV; ++u) cur[u] = nxt[u];
+        }
       }
+    else
+      for (uint32_t q = warp; q < (uint32_t)NTHREADS; q += NWARPS)
+        {
+        const uint32_t nbytes = sh_size[q];
+        if (nbytes) warp_copy_global(a.payload + base + sh_off[q], cta_scr + (size_t)q * a.slot, nbytes);
+        }
     }
   }
 
