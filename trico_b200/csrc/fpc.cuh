@@ -22,6 +22,8 @@
 
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace tb200 {
 
 template <typename W> struct FpcTraits;
@@ -189,15 +191,7 @@ __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride,
   return obase;
   }
 
-// ---------------------------------------------------------------------------------------------
-// K3: chunked encode, fused with the AoS -> SoA transpose and the archive assembly.
-// Tile = KT = 12/NCOMP consecutive chunk ranges x NCOMP components = 12 chunks, one warp each.
-//   1. the CTA stages the tile's AoS elements in shared memory with 16-byte coalesced loads
-//      (this is the reference's trico_transpose_*_aos_to_soa, transpose_aos_to_soa.c:8-82, fused)
-//   2. every warp encodes its chunk into a shared-memory slot
-//   3. chunk sizes -> block prefix -> decoupled look-back over tiles -> payload written once, at
-//      its final offset; the u16 size table and the stream header are written by the same kernel.
-// ---------------------------------------------------------------------------------------------
+// arguments of the chunked encoder (K3, fpc_encode_lanes_kernel below)
 struct FpcEncodeArgs
   {
   const void* in;          // device, AoS: n * ncomp words
@@ -214,98 +208,6 @@ struct FpcEncodeArgs
   uint8_t* scratch;        // lane-per-chunk kernel: one slot per chunk in flight (grid * chunks per tile)
   uint32_t slot;           // bytes per scratch slot (multiple of 16, >= chunk bound + 16)
   };
-
-constexpr int FPC_ENC_WARPS = 12;
-
-template <typename W, int NCOMP>
-__global__ void __launch_bounds__(FPC_ENC_WARPS * 32)
-fpc_encode_kernel(const FpcEncodeArgs a)
-  {
-  constexpr int KT = FPC_ENC_WARPS / NCOMP;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const uint32_t S = 1u << a.log2S;
-  const uint32_t slot = (fpc_chunk_bound(S, sizeof(W)) + 15u + 16u) & ~15u;
-  W* tile_in = reinterpret_cast<W*>(smem_raw);                                   // KT*S*NCOMP words
-  uint8_t* stage = smem_raw + (size_t)FPC_ENC_WARPS * S * sizeof(W);             // 12 slots
-  W* tables = reinterpret_cast<W*>(stage + (size_t)FPC_ENC_WARPS * slot);        // per warp T1|T2
-  __shared__ uint32_t sh_tile;
-  __shared__ uint32_t sh_size[FPC_ENC_WARPS];
-  __shared__ uint32_t sh_off[FPC_ENC_WARPS];
-  __shared__ uint64_t sh_base;
-
-  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-  if (threadIdx.x == 0) sh_tile = atomicAdd(a.ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = sh_tile;
-
-  // 1. stage the AoS tile
-  const uint64_t k0 = (uint64_t)tile * KT;
-  const uint64_t v_lo = k0 << a.log2S;
-  uint64_t v_hi = (k0 + KT) << a.log2S; if (v_hi > a.n) v_hi = a.n;
-  const uint32_t nwords = (uint32_t)(v_hi - v_lo) * NCOMP;
-  const W* gin = reinterpret_cast<const W*>(a.in) + v_lo * NCOMP;
-  if ((reinterpret_cast<uintptr_t>(gin) & 15u) == 0)
-    {
-    constexpr int PER = 16 / sizeof(W);
-    const uint32_t nvec = nwords / PER;
-    const uint4* g4 = reinterpret_cast<const uint4*>(gin);
-    uint4* s4 = reinterpret_cast<uint4*>(tile_in);
-    for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) s4[i] = __ldg(g4 + i);
-    for (uint32_t i = nvec * PER + threadIdx.x; i < nwords; i += blockDim.x) tile_in[i] = gin[i];
-    }
-  else
-    for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) tile_in[i] = gin[i];
-  __syncthreads();
-
-  // 2. one chunk per warp
-  const uint32_t kk = warp / NCOMP, c = warp % NCOMP;
-  const uint64_t k = k0 + kk;
-  uint32_t nbytes = 0;
-  if (k < a.nranges)
-    {
-    const uint64_t lo = k << a.log2S;
-    const uint32_t cnt = (uint32_t)((a.n - lo < S) ? (a.n - lo) : S);
-    W* T1 = tables + (size_t)warp * ((1u << a.e1) + (1u << a.e2));
-    W* T2 = T1 + (1u << a.e1);
-    nbytes = fpc_encode_warp<W, true>(tile_in + (size_t)kk * S * NCOMP + c, NCOMP, cnt, stage + (size_t)warp * slot, T1, T2, a.e1, a.e2);
-    }
-  if (lane == 0) sh_size[warp] = nbytes;
-  __syncthreads();
-
-  // 3. offsets and assembly.  Chunk order in the stream is (range, component) = warp order.
-  if (warp == 0)
-    {
-    uint32_t mine = lane < FPC_ENC_WARPS ? sh_size[lane] : 0, incl = mine;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1)
-      {
-      const uint32_t up = __shfl_up_sync(FULL, incl, o);
-      if (lane >= (unsigned)o) incl += up;
-      }
-    if (lane < FPC_ENC_WARPS) sh_off[lane] = incl - mine;
-    const uint64_t agg = __shfl_sync(FULL, incl, FPC_ENC_WARPS - 1);
-    const uint64_t excl = lookback_exclusive(a.desc, tile, agg);
-    if (lane == 0)
-      {
-      sh_base = excl;
-      if (tile == a.ntiles - 1)
-        {
-        *a.total = excl + agg;
-        store_u64_bytes(a.total_field, excl + agg);
-        }
-      }
-    }
-  __syncthreads();
-  if (k < a.nranges)
-    {
-    warp_copy_smem_to_global(a.payload + sh_base + sh_off[warp], stage + (size_t)warp * slot, nbytes);
-    if (lane == 0)
-      {
-      uint8_t* sz = a.sizes + 2 * (k * NCOMP + c);
-      sz[0] = (uint8_t)nbytes; sz[1] = (uint8_t)(nbytes >> 8);
-      }
-    }
-  }
 
 // ---------------------------------------------------------------------------------------------
 // Legacy (reference v0) stream encoder: one warp per component stream, whole stream as one chain,
@@ -550,10 +452,9 @@ fpc_decode_kernel(const FpcDecodeArgs a)
     const uint32_t bp0 = relA & 15u;
     uint32_t bp = bp0;
     const uint32_t todo = (i0 < cnt) ? ((cnt - i0 < (uint32_t)SB) ? cnt - i0 : (uint32_t)SB) : 0;
-#pragma unroll 1
-    for (uint32_t g = 0; g < (uint32_t)SB / TR::GROUP; ++g)
+    auto decode_group = [&](uint32_t g, auto checked)
       {
-      if (g * TR::GROUP >= todo) break;
+      constexpr bool CHECK = decltype(checked)::value;
       // code word
       uint32_t bc;
         {
@@ -584,11 +485,25 @@ fpc_decode_kernel(const FpcDecodeArgs a)
           }
         bp += nb;
         const uint32_t idx = g * TR::GROUP + jj;
-        if (idx < todo)
+        if (!CHECK || idx < todo)
           {
           const W v = fpc_decode_value<W, 32>(st, x, use2, T1, T2, a.e1, a.e2, m2);
           *reinterpret_cast<W*>(srow + (size_t)idx * NCOMP * WPV) = v;
           }
+        }
+      };
+    if (__all_sync(FULL, todo == (uint32_t)SB))
+      { // every lane has a full sub-block: no per-value bounds checks
+#pragma unroll 1
+      for (uint32_t g = 0; g < (uint32_t)SB / TR::GROUP; ++g) decode_group(g, std::false_type{});
+      }
+    else
+      {
+#pragma unroll 1
+      for (uint32_t g = 0; g < (uint32_t)SB / TR::GROUP; ++g)
+        {
+        if (g * TR::GROUP >= todo) break;
+        decode_group(g, std::true_type{});
         }
       }
     relA += bp - bp0;
@@ -733,6 +648,19 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
   uint8_t* my_scr = cta_scr + (size_t)(klocal * NCOMP + c) * a.slot;
   const uint8_t* gin = reinterpret_cast<const uint8_t*>(a.in);
   const bool in_aligned = (reinterpret_cast<uintptr_t>(gin) & 15u) == 0;
+  // L2 residency: the input is read once (evict first); the scratch slots are written now and read
+  // back at the end of the tile (evict last when written, evict first when read back)
+  uint64_t pol_first, pol_last;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+  auto st_scratch = [&](uint8_t* p, const uint4 v)
+    { asm volatile("st.global.cg.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol_last) : "memory"); };
+  auto ld_scratch = [&](const uint4* p)
+    {
+    uint4 w;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p), "l"(pol_first) : "memory");
+    return w;
+    };
 
   for (;;)
     {
@@ -768,7 +696,7 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
         for (uint32_t ci = threadIdx.x; ci < 32u * R * ROWV; ci += NTHREADS)
           {
           const uint32_t r = ci / (uint32_t)ROWV, v = ci - r * (uint32_t)ROWV;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(stage_s + (r * ROWW + 4u * v) * 4u), "l"(tin + (size_t)r * row_bytes + 16u * v) : "memory");
+          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(stage_s + (r * ROWW + 4u * v) * 4u), "l"(tin + (size_t)r * row_bytes + 16u * v), "l"(pol_first) : "memory");
           }
         }
       else
@@ -796,10 +724,9 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
 
       // b. encode up to SB values of this lane's chunk
       const uint32_t todo = (i0 < cnt) ? ((cnt - i0 < (uint32_t)SB) ? cnt - i0 : (uint32_t)SB) : 0;
-#pragma unroll 1
-      for (uint32_t g = 0; g < (uint32_t)SB / TR::GROUP; ++g)
+      auto encode_group = [&](uint32_t g, auto checked)
         {
-        if (g * TR::GROUP >= todo) break;
+        constexpr bool CHECK = decltype(checked)::value;
         W xs[TR::GROUP];
         uint32_t nbs[TR::GROUP];
         uint32_t bc = 0;
@@ -809,7 +736,7 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
           const uint32_t idx = g * TR::GROUP + jj;
           uint32_t code = 1, nb = 1;                                // pad slot of the last group: code 1 + one zero byte (fpc.c:196-204, :789-794)
           W x = 0;
-          if (idx < todo)
+          if (!CHECK || idx < todo)
             {
             const W v = *reinterpret_cast<const W*>(srow + (size_t)idx * NCOMP * WPV);
             const W x1 = v ^ pred1, x2 = v ^ pred2;
@@ -852,6 +779,20 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
             fpc_emit(wrow, acc, fill, wp, second, nb > 4u ? nb - 4u : 0u);
             }
           }
+        };
+      if (__all_sync(FULL, todo == (uint32_t)SB))
+        { // every lane has a full sub-block: no per-value bounds checks, no pad slots
+#pragma unroll 1
+        for (uint32_t g = 0; g < (uint32_t)SB / TR::GROUP; ++g) encode_group(g, std::false_type{});
+        }
+      else
+        {
+#pragma unroll 1
+        for (uint32_t g = 0; g < (uint32_t)SB / TR::GROUP; ++g)
+          {
+          if (g * TR::GROUP >= todo) break;
+          encode_group(g, std::true_type{});
+          }
         }
       __syncthreads();                               // the staging tile may be overwritten; window words are visible
       if (i0 + SB < cnt0) stage_in(i0 + SB);         // next slab crosses L2 -> shared memory while the windows drain
@@ -865,7 +806,7 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
         const uint32_t L = ci / (uint32_t)WV, v = ci - L * (uint32_t)WV;
         const uint32_t nfL = __shfl_sync(FULL, nf, L), posL = __shfl_sync(FULL, flushed, L);
         if (v < nfL)
-          __stcg(reinterpret_cast<uint4*>(cta_scr + (size_t)((rgrp * 32 + L) * NCOMP + c) * a.slot + posL + 16u * v), wwarp4[ci]);
+          st_scratch(cta_scr + (size_t)((rgrp * 32 + L) * NCOMP + c) * a.slot + posL + 16u * v, wwarp4[ci]);
         }
       __syncwarp();
       if (nf)
@@ -889,7 +830,7 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
       if (fill) wrow[wp] = acc;
       const uint32_t tailb = 4u * wp + fill;                          // < 16
       total = flushed + tailb;
-      if (tailb) __stcg(reinterpret_cast<uint4*>(my_scr + flushed), *reinterpret_cast<const uint4*>(wrow));
+      if (tailb) st_scratch(my_scr + flushed, *reinterpret_cast<const uint4*>(wrow));
       }
     sh_size[klocal * NCOMP + c] = total;
     __syncthreads();
@@ -942,7 +883,7 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
         const uint32_t nv = (sh_size[q] + 15u) >> 4;
         const uint4* s4 = reinterpret_cast<const uint4*>(cta_scr + (size_t)q * a.slot);
 #pragma unroll
-        for (int u = 0; u < BV; ++u) if (lane + 32u * u < nv) r[u] = __ldcg(s4 + lane + 32 * u);
+        for (int u = 0; u < BV; ++u) if (lane + 32u * u < nv) r[u] = ld_scratch(s4 + lane + 32 * u);
         };
       if (warp < (unsigned)NTHREADS) fetch(cur, warp);
       for (uint32_t q = warp; q < (uint32_t)NTHREADS; q += NWARPS)
