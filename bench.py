@@ -339,9 +339,9 @@ def run_b200(args):
             return e0.elapsed_time(e1) / n / 1e3
         nrep = max(3, min(args.steps, 10))
         specs = {
-            "fpc_encode_kernel<u32,3>": (lambda: d.encode_stream_device(1, verts.data_ptr(), nv, enc_v.data_ptr(), cap_v, sizes.data_ptr(), l2v), raw_v, bytes_v),
-            "lz4_encode_kernel<4>": (lambda: d.encode_stream_device(3, tris.data_ptr(), nt, enc_t.data_ptr(), cap_t, sizes.data_ptr() + 8, l2t), raw_t, bytes_t),
-            "fpc_decode_kernel<u32,3>": (lambda: d.decode_stream_device(hdr_v, enc_v.data_ptr(), bytes_v, out_v.data_ptr()), raw_v, bytes_v),
+            "fpc_encode_lanes_kernel<u32,3,1,32>": (lambda: d.encode_stream_device(1, verts.data_ptr(), nv, enc_v.data_ptr(), cap_v, sizes.data_ptr(), l2v), raw_v, bytes_v),
+            "lz4_encode_kernel<4,10>+lz4_assemble_kernel": (lambda: d.encode_stream_device(3, tris.data_ptr(), nt, enc_t.data_ptr(), cap_t, sizes.data_ptr() + 8, l2t), raw_t, bytes_t),
+            "fpc_decode_kernel<u32,3,1,32>": (lambda: d.decode_stream_device(hdr_v, enc_v.data_ptr(), bytes_v, out_v.data_ptr()), raw_v, bytes_v),
             "lz4_decode_kernel<4>": (lambda: d.decode_stream_device(hdr_t, enc_t.data_ptr(), bytes_t, out_t.data_ptr()), raw_t, bytes_t),
         }
         for name, (fn, r, c) in specs.items():
@@ -460,6 +460,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"C2 synthetic float mesh: {nv} vertices + {nt} uint32 triangles per GPU ({W}x{H} jittered grid, ids shuffled in blocks of 64)",
                    "raw_bytes_per_gpu": raw, "fpc_chunk_values": 1 << l2v, "lz4_block_bytes": 1 << l2t, "fpc_exponents": [2, 4],
+                   "lz4_hash_entries": 1024, "e2e_host_pipeline": "32 MiB slabs, H2D / kernels / D2H on three streams",
                    "l2": "inputs (3.6 GB) are larger than L2; no flush needed", "sharding": f"{world} x whole mesh, chunk-sharded, size exchange only",
                    "gpu": devname},
         "encode_gbs": round(enc_gbs, 2), "decode_gbs": round(dec_gbs, 2),

@@ -208,6 +208,7 @@ static int launch_fpc_encode_lanes(tb200_ctx* c, FpcEncodeArgs a)
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
   if (per_sm < 1) return fail_msg("fpc_encode_lanes_kernel does not fit on an SM");
   // persistent grid, every CTA resident (the look-back relies on it); a CTA reuses its scratch slots
+  if (const char* e = getenv("TB200_FPC_ENC_CTAS")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments
   uint32_t grid = (uint32_t)per_sm * (uint32_t)sms;
   if (grid > a.ntiles) grid = a.ntiles;
   a.slot = (fpc_chunk_bound(S, sizeof(W)) + 16u + 15u) & ~15u;
