@@ -15,7 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libtrico_b200.so")
+# TRICO_B200_LIB selects another build of the same sources (kernel experiments: see build_variant)
+LIB = os.environ.get("TRICO_B200_LIB") or os.path.join(LIBDIR, "libtrico_b200.so")
 ROOT = os.path.dirname(HERE)
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -70,5 +71,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defs, verbose: bool = False) -> str:
+    """Experiment build: the same sources with extra -D definitions -> lib/libtrico_b200_<name>.so
+    (load it with TRICO_B200_LIB=<path>)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    nvcc = _nvcc()
+    inc = ["-I", os.path.join(ROOT, "include")]
+    obj_c = os.path.join(LIBDIR, "archive.o")
+    obj_cu = os.path.join(LIBDIR, f"device_api_{name}.o")
+    out = os.path.join(LIBDIR, f"libtrico_b200_{name}.so")
+    dd = [f"-D{d}" for d in defs]
+    cmds = [
+        [os.environ.get("CC", "gcc"), *CC_FLAGS, *inc, "-c", os.path.join(CSRC, "archive.c"), "-o", obj_c],
+        [nvcc, *NVCC_FLAGS, *dd, *inc, "-c", os.path.join(CSRC, "device_api.cu"), "-o", obj_cu],
+        [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, obj_c, obj_cu, "-lcudart"],
+    ]
+    for cmd in cmds:
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+    os.remove(obj_cu)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:], verbose=True))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

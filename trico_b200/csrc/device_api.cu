@@ -65,6 +65,8 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, void* cuda_stream)
     c->own_stream = true;
     }
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  // (Measured: reserving a persisting L2 carve-out for the encoders' evict_last scratch lines makes
+  // every kernel slower - C2 FPC decode 0.59 -> 1.18 ms - so the device default, none, stays.)
   return c;
   }
 
@@ -127,7 +129,8 @@ template <typename K>
 static int set_smem(K kernel, size_t bytes, const tb200_ctx* c)
   {
   if (bytes > (size_t)c->max_smem_optin) return fail_msg("kernel needs more shared memory than the device offers");
-  if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // (static + dynamic) above 48 KiB needs the opt-in; the kernels carry up to ~2 KiB of static shared memory
+  if (bytes > 40 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 1;
   }
 
@@ -190,21 +193,24 @@ extern "C" uint64_t tb200_v1_stream_bound(int type, uint32_t count, int log2_chu
 // ------------------------------------------------------------------------------------------------
 // chunked FPC
 // ------------------------------------------------------------------------------------------------
-template <typename W, int NCOMP, int R, int SB>
+template <typename W, int NCOMP, int R, int SB, int EXP = -1>
 static int launch_fpc_encode_lanes(tb200_ctx* c, FpcEncodeArgs a)
   {
-  using WIN = FpcWindow<W, SB>;
+  if (EXP < 0)   // the archive default exponents run a build with the shifts and masks compiled in
+    return (a.e1 == 2 && a.e2 == 4) ? launch_fpc_encode_lanes<W, NCOMP, R, SB, 0x0204>(c, a) : launch_fpc_encode_lanes<W, NCOMP, R, SB, 0>(c, a);
+  constexpr int EX = EXP < 0 ? 0 : EXP;
+  using WIN = FpcEncWindow<W, SB>;
   constexpr int NWARPS = NCOMP * R;
   const uint32_t S = 1u << a.log2S;
   a.ntiles = (a.nranges + 32 * R - 1) / (32 * R);
   if (!ws_prepare(c, a.ntiles + 1, &a.ticket, &a.desc)) return 0;
   if (!a.total_field) a.total_field = reinterpret_cast<uint8_t*>(a.desc + a.ntiles);
   const size_t smem = (size_t)NWARPS * 32 * WIN::VECS * 16 +
-                      (size_t)32 * R * (SB * NCOMP * (sizeof(W) / 4) + 4) * 4 +
+                      (size_t)32 * R * fpc_stage_row_words_enc(SB, NCOMP, sizeof(W)) * 4 +
                       (size_t)NWARPS * 32 * ((1u << a.e1) + (1u << a.e2)) * sizeof(W);
-  if (!set_smem(fpc_encode_lanes_kernel<W, NCOMP, R, SB>, smem, c)) return 0;
+  if (!set_smem(fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX>, smem, c)) return 0;
   int per_sm = 0, sms = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc_encode_lanes_kernel<W, NCOMP, R, SB>, NWARPS * 32, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX>, NWARPS * 32, smem));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
   if (per_sm < 1) return fail_msg("fpc_encode_lanes_kernel does not fit on an SM");
   // persistent grid, every CTA resident (the look-back relies on it); a CTA reuses its scratch slots
@@ -215,7 +221,7 @@ static int launch_fpc_encode_lanes(tb200_ctx* c, FpcEncodeArgs a)
   uint8_t* scratch = nullptr;
   if (!big_prepare(c, (size_t)grid * NWARPS * 32 * a.slot + 64, &scratch)) return 0;
   a.scratch = scratch;
-  fpc_encode_lanes_kernel<W, NCOMP, R, SB><<<grid, NWARPS * 32, smem, c->stream>>>(a);
+  fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX><<<grid, NWARPS * 32, smem, c->stream>>>(a);
   c->launches++;
   CK(cudaGetLastError());
   return 1;
@@ -244,18 +250,21 @@ extern "C" int tb200_fpc_encode(tb200_ctx* c, int wordsize, int ncomp, const voi
   return ncomp == 3 ? launch_fpc_encode_lanes<uint64_t, 3, 1, 16>(c, a) : ncomp == 2 ? launch_fpc_encode_lanes<uint64_t, 2, 2, 16>(c, a) : launch_fpc_encode_lanes<uint64_t, 1, 4, 16>(c, a);
   }
 
-template <typename W, int NCOMP, int R, int SB>
+template <typename W, int NCOMP, int R, int SB, int EXP = -1>
 static int launch_fpc_decode(tb200_ctx* c, FpcDecodeArgs a)
   {
+  if (EXP < 0)
+    return (a.e1 == 2 && a.e2 == 4) ? launch_fpc_decode<W, NCOMP, R, SB, 0x0204>(c, a) : launch_fpc_decode<W, NCOMP, R, SB, 0>(c, a);
+  constexpr int EX = EXP < 0 ? 0 : EXP;
   using WIN = FpcWindow<W, SB>;
   constexpr int NWARPS = NCOMP * R;
   a.ntiles = (a.nranges + 32 * R - 1) / (32 * R);
   if (!ws_prepare(c, a.ntiles, &a.ticket, &a.desc)) return 0;
   const size_t smem = (size_t)NWARPS * 32 * WIN::VECS * 16 +
-                      (size_t)32 * R * (SB * NCOMP * (sizeof(W) / 4) + 4) * 4 +
+                      (size_t)32 * R * fpc_stage_row_words(SB, NCOMP, sizeof(W)) * 4 +
                       (size_t)NWARPS * 32 * ((1u << a.e1) + (1u << a.e2)) * sizeof(W);
-  if (!set_smem(fpc_decode_kernel<W, NCOMP, R, SB>, smem, c)) return 0;
-  fpc_decode_kernel<W, NCOMP, R, SB><<<a.ntiles, NWARPS * 32, smem, c->stream>>>(a);
+  if (!set_smem(fpc_decode_kernel<W, NCOMP, R, SB, EX>, smem, c)) return 0;
+  fpc_decode_kernel<W, NCOMP, R, SB, EX><<<a.ntiles, NWARPS * 32, smem, c->stream>>>(a);
   c->launches++;
   CK(cudaGetLastError());
   return 1;

@@ -53,6 +53,13 @@ __host__ __device__ constexpr uint32_t fpc_chunk_bound(uint32_t values, int wbyt
                      : values * 8u + ((values + 1u) / 2u) + 2u;
   }
 
+// words between consecutive rows of the staging tile (row = chunk range = lane).  Odd, so that the
+// 32 lanes of a warp, each on the same word of its own row, hit 32 different banks.
+__host__ __device__ constexpr int fpc_stage_row_words(int sb, int ncomp, int wbytes) { return sb * ncomp * (wbytes / 4) + 1; }
+// the encoder fills its tile with 16-byte cp.async copies, so its rows stay 16-byte aligned (and
+// its per-value reads see a 4-way bank conflict; 4-byte copies into odd rows cost more than that)
+__host__ __device__ constexpr int fpc_stage_row_words_enc(int sb, int ncomp, int wbytes) { return sb * ncomp * (wbytes / 4) + 4; }
+
 __device__ __forceinline__ int sig_bytes(uint32_t x) { return (39 - __clz((int)x)) >> 3; }
 __device__ __forceinline__ int sig_bytes(uint64_t x) { return (71 - __clzll((long long)x)) >> 3; }
 
@@ -314,6 +321,10 @@ struct FpcDecodeArgs
   uint32_t* ticket;        // zeroed
   };
 
+#ifndef TB200_FPC_DEC_WORDBUF
+#define TB200_FPC_DEC_WORDBUF 1
+#endif
+
 template <typename W, int SB> struct FpcWindow
   {
   using TR = FpcTraits<W>;
@@ -324,21 +335,33 @@ template <typename W, int SB> struct FpcWindow
   static constexpr int VECS = (BYTES + 15) / 16;
   };
 
-template <typename W, int NCOMP, int R, int SB>
+// The encoder's window holds the carried tail of the previous sub-block (< 16 bytes) plus everything
+// one sub-block can produce (code words + SB full residuals); nothing is read past it.
+template <typename W, int SB> struct FpcEncWindow
+  {
+  using TR = FpcTraits<W>;
+  static constexpr int BYTES = 15 + (SB / TR::GROUP) * TR::HDR + SB * TR::WBYTES;
+  static constexpr int VECS = (BYTES + 15) / 16;
+  };
+
+// EXP = (e1 << 8) | e2 compiles the predictor exponents in (the archive default (2,4) runs this
+// way: shifts and masks become immediates); EXP = 0 takes them from the arguments.
+template <typename W, int NCOMP, int R, int SB, int EXP>
 __global__ void __launch_bounds__(NCOMP * R * 32)
 fpc_decode_kernel(const FpcDecodeArgs a)
   {
+  const int e1 = EXP ? (EXP >> 8) : a.e1, e2 = EXP ? (EXP & 255) : a.e2;
   using TR = FpcTraits<W>;
   using WIN = FpcWindow<W, SB>;
   constexpr int NWARPS = NCOMP * R;
   constexpr int NTHREADS = NWARPS * 32;
   constexpr int WV = WIN::VECS;                           // 16-byte vectors per lane window
   constexpr int WPV = sizeof(W) / 4;                      // 32-bit words per value
-  constexpr int ROWV = SB * NCOMP * WPV / 4;              // 16-byte vectors per staged row
-  constexpr int ROWW = SB * NCOMP * WPV + 4;              // staging row stride in words (rows stay 16-byte aligned)
-  static_assert((SB * NCOMP * WPV) % 4 == 0, "staged rows must be whole vectors");
+  constexpr int ROWLEN = SB * NCOMP * WPV;                // words per staged row
+  constexpr int ROWW = fpc_stage_row_words(SB, NCOMP, sizeof(W));   // odd row stride: lane = row, so bank = lane + word
+  static_assert(NTHREADS % ROWLEN == 0 && NTHREADS / ROWLEN == R, "one thread per row word, R rows per pass");
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const uint32_t nt1 = 1u << a.e1, nt2 = 1u << a.e2;
+  const uint32_t nt1 = 1u << e1, nt2 = 1u << e2;
   uint32_t* win = reinterpret_cast<uint32_t*>(smem_raw);                               // [NWARPS][32][WV*4]
   uint32_t* stagebuf = win + (size_t)NWARPS * 32 * WV * 4;                             // [32*R][ROWW]
   W* tables = reinterpret_cast<W*>(stagebuf + (size_t)32 * R * ROWW);                  // [NWARPS][nt1+nt2][32]
@@ -419,25 +442,44 @@ fpc_decode_kernel(const FpcDecodeArgs a)
   const uint32_t wwarp_s = (uint32_t)__cvta_generic_to_shared(win + (size_t)warp * 32 * WV * 4);
   uint32_t* srow = stagebuf + (size_t)klocal * ROWW + c * WPV;
   uint8_t* gout = reinterpret_cast<uint8_t*>(a.out);
-  const bool out_aligned = (reinterpret_cast<uintptr_t>(gout) & 15u) == 0;
+  const bool out_aligned = (reinterpret_cast<uintptr_t>(gout) & 3u) == 0;
 
   // Window refill: the warp's 32 windows are contiguous in shared memory ([lane][WV] vectors), so
   // copy number ci lands at vector ci; its source is vector ci % WV of lane ci / WV's window.
   // 16-byte cp.async copies (global -> shared without a register round trip), all in flight at once;
   // bytes at or beyond the end of the payload are not read (src-size operand, zero filled).
+  uint32_t fsrc[WV];                                       // copy `it` of this lane: source lane | 16 * vector << 8
+#pragma unroll
+  for (int it = 0; it < WV; ++it)
+    {
+    const uint32_t ci = (uint32_t)it * 32u + lane;
+    const uint32_t L = ci / (uint32_t)WV;
+    fsrc[it] = L | ((16u * (ci - L * (uint32_t)WV)) << 8);
+    }
   auto fill = [&]()
     {
     const uint32_t arel = relA & ~15u;
+    if (__all_sync(FULL, arel + 16u * WV <= endoff))
+      { // every window of the warp ends inside the payload (all but the stream's last tiles)
 #pragma unroll
-    for (int it = 0; it < WV; ++it)
+      for (int it = 0; it < WV; ++it)
+        {
+        const uint32_t off = __shfl_sync(FULL, arel, fsrc[it] & 31u) + (fsrc[it] >> 8);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(wwarp_s + 16u * ((uint32_t)it * 32u + lane)), "l"(tb16 + off) : "memory");
+        }
+      }
+    else
       {
-      const uint32_t ci = (uint32_t)it * 32u + lane;
-      const uint32_t L = ci / (uint32_t)WV, v = ci - L * (uint32_t)WV;
-      const uint32_t off = __shfl_sync(FULL, arel, L) + 16u * v;
-      const int32_t rem = (int32_t)endoff - (int32_t)off;
-      const uint32_t ssz = rem >= 16 ? 16u : (rem > 0 ? (uint32_t)rem : 0u);
-      const uint32_t offc = off < last16 ? off : last16;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(wwarp_s + 16u * ci), "l"(tb16 + offc), "r"(ssz) : "memory");
+#pragma unroll
+      for (int it = 0; it < WV; ++it)
+        {
+        const uint32_t ci = (uint32_t)it * 32u + lane;
+        const uint32_t off = __shfl_sync(FULL, arel, fsrc[it] & 31u) + (fsrc[it] >> 8);
+        const int32_t rem = (int32_t)endoff - (int32_t)off;
+        const uint32_t ssz = rem >= 16 ? 16u : (rem > 0 ? (uint32_t)rem : 0u);
+        const uint32_t offc = off < last16 ? off : last16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(wwarp_s + 16u * ci), "l"(tb16 + offc), "r"(ssz) : "memory");
+        }
       }
     asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -452,7 +494,65 @@ fpc_decode_kernel(const FpcDecodeArgs a)
     const uint32_t bp0 = relA & 15u;
     uint32_t bp = bp0;
     const uint32_t todo = (i0 < cnt) ? ((cnt - i0 < (uint32_t)SB) ? cnt - i0 : (uint32_t)SB) : 0;
-    auto decode_group = [&](uint32_t g, auto checked)
+    // 32-bit values keep their read position in BITS (pos8, relative to the window start): the
+    // shift counts of the extraction are then plain register operands.
+    uint32_t pos8 = 8u * bp0;
+#if TB200_FPC_DEC_WORDBUF
+    // The lane walks its window through a three-word big-endian register buffer (q0 = word holding
+    // the next unread byte, q1, q2 = the two behind it; pb8 = bits of q0 already consumed).  A fetch
+    // is two funnel shifts on q0:q1; when it crosses into q1 the buffer advances and ONE word is
+    // loaded - into q2, i.e. a whole word before it can be needed - so a value costs about one
+    // shared-memory read instead of the two of an unaligned fetch, off the dependency chain.
+    uint32_t q0 = 0, q1 = 0, q2 = 0, pb8 = pos8 & 31u;
+    const uint32_t* qn = wrow + (bp0 >> 2) + 3;
+    if (sizeof(W) == 4)
+      {
+      q0 = __byte_perm(qn[-3], 0u, 0x0123u); q1 = __byte_perm(qn[-2], 0u, 0x0123u); q2 = __byte_perm(qn[-1], 0u, 0x0123u);
+      }
+#endif
+    auto take = [&](uint32_t nb8) -> uint32_t
+      { // the next nb8 / 8 (0..4) bytes as a big-endian number
+#if TB200_FPC_DEC_WORDBUF
+      const uint32_t t = __funnelshift_l(q1, q0, pb8);
+      const uint32_t x = __funnelshift_lc(t, 0u, nb8);
+      pb8 += nb8;
+      if (pb8 >= 32u)
+        {
+        q0 = q1; q1 = q2;
+        q2 = __byte_perm(*qn++, 0u, 0x0123u);
+        }
+      pb8 &= 31u;
+      return x;
+#else
+      const uint32_t* w = wrow + (pos8 >> 5);
+      const uint32_t t = __funnelshift_r(w[0], w[1], pos8);             // shift count taken modulo 32
+      pos8 += nb8;
+      return __funnelshift_lc(__byte_perm(t, 0u, 0x0123u), 0u, nb8);
+#endif
+      };
+    auto decode_group32 = [&](uint32_t g, auto checked)
+      { // fpc.c:248-326.  The eight 3-bit codes are split once per group: bit 3j of `two` = value j
+        // takes the DFCM prediction (code > 4), and the residual lengths in bits (8 * (code, or
+        // code - 4): clearing bit 2 of codes 5..7) sit in bits 3j+3..3j+5 of `len8`.
+      constexpr bool CHECK = decltype(checked)::value;
+      const uint32_t bc = take(24u);
+      const uint32_t two = (bc >> 2) & ((bc >> 1) | bc) & 0x249249u;
+      const uint32_t len8 = (bc & ~(two << 2)) << 3;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        {
+        const uint32_t nb8 = (len8 >> (3 * jj)) & 0x38u;
+        const bool use2 = (two >> (3 * jj)) & 1u;
+        const W x = (W)take(nb8);
+        const uint32_t idx = g * 8u + jj;
+        if (!CHECK || idx < todo)
+          {
+          const W v = fpc_decode_value<W, 32>(st, x, use2, T1, T2, e1, e2, m2);
+          srow[idx * NCOMP * WPV] = (uint32_t)v;
+          }
+        }
+      };
+    auto decode_group64 = [&](uint32_t g, auto checked)
       {
       constexpr bool CHECK = decltype(checked)::value;
       // code word
@@ -469,28 +569,24 @@ fpc_decode_kernel(const FpcDecodeArgs a)
         const uint32_t code = (bc >> (TR::CBITS * jj)) & ((1u << TR::CBITS) - 1u);
         const bool use2 = code > (uint32_t)TR::BASE2;
         const uint32_t nb = use2 ? code - TR::BASE2 : code;
-        W x;
         const uint32_t wi = bp >> 2;
         const uint32_t sel = 0x0123u + (bp & 3u) * 0x1111u;
-        if (sizeof(W) == 4)
-          {
-          const uint32_t be = __byte_perm(wrow[wi], wrow[wi + 1], sel);
-          x = (W)__funnelshift_lc(be, 0u, 8u * nb);
-          }
-        else
-          {
-          const uint32_t w0 = wrow[wi], w1 = wrow[wi + 1], w2 = wrow[wi + 2];
-          const uint64_t be = ((uint64_t)__byte_perm(w0, w1, sel) << 32) | __byte_perm(w1, w2, sel);
-          x = nb ? (W)(be >> (64 - 8 * nb)) : (W)0;
-          }
+        const uint32_t w0 = wrow[wi], w1 = wrow[wi + 1], w2 = wrow[wi + 2];
+        const uint64_t be = ((uint64_t)__byte_perm(w0, w1, sel) << 32) | __byte_perm(w1, w2, sel);
+        const W x = nb ? (W)(be >> (64 - 8 * nb)) : (W)0;
         bp += nb;
         const uint32_t idx = g * TR::GROUP + jj;
         if (!CHECK || idx < todo)
           {
-          const W v = fpc_decode_value<W, 32>(st, x, use2, T1, T2, a.e1, a.e2, m2);
-          *reinterpret_cast<W*>(srow + (size_t)idx * NCOMP * WPV) = v;
+          const W v = fpc_decode_value<W, 32>(st, x, use2, T1, T2, e1, e2, m2);
+          srow[idx * NCOMP * WPV] = (uint32_t)v;
+          srow[idx * NCOMP * WPV + 1] = (uint32_t)((uint64_t)v >> 32);
           }
         }
+      };
+    auto decode_group = [&](uint32_t g, auto checked)
+      {
+      if (sizeof(W) == 4) decode_group32(g, checked); else decode_group64(g, checked);
       };
     if (__all_sync(FULL, todo == (uint32_t)SB))
       { // every lane has a full sub-block: no per-value bounds checks
@@ -506,6 +602,14 @@ fpc_decode_kernel(const FpcDecodeArgs a)
         decode_group(g, std::true_type{});
         }
       }
+    if (sizeof(W) == 4)
+      {
+#if TB200_FPC_DEC_WORDBUF
+      bp = 4u * (uint32_t)(qn - wrow - 3) + (pb8 >> 3);
+#else
+      bp = pos8 >> 3;
+#endif
+      }
     relA += bp - bp0;
     // the next window crosses L2 -> shared memory while the slab is flushed
     if (i0 + SB < cnt0) fill();
@@ -513,14 +617,22 @@ fpc_decode_kernel(const FpcDecodeArgs a)
 
     // c. flush the staged slab: row r = range (tile*32R + r), values [i0, i0+SB) x NCOMP, contiguous
     if (full_tile && out_aligned)
-      {
-      uint8_t* tile_out = gout + ((((uint64_t)tile * (32 * R)) << a.log2S) + i0) * (NCOMP * sizeof(W));
+      { // thread t moves word t % ROWLEN of rows t / ROWLEN, + R, + 2R, ...: consecutive lanes read
+        // consecutive shared-memory words (no bank conflicts: the row stride is odd) and write
+        // consecutive global words (whole 128-byte lines per warp store)
+      const uint32_t w = threadIdx.x % (uint32_t)ROWLEN, r0 = threadIdx.x / (uint32_t)ROWLEN;
       const uint32_t row_bytes = (uint32_t)(NCOMP * sizeof(W)) << a.log2S;
-      for (uint32_t ci = threadIdx.x; ci < 32u * R * ROWV; ci += NTHREADS)
+      uint8_t* to = gout + ((((uint64_t)tile * (32 * R)) << a.log2S) + i0) * (NCOMP * sizeof(W)) + (size_t)r0 * row_bytes + 4u * w;
+      const uint32_t* from = stagebuf + (size_t)r0 * ROWW + w;
+      constexpr int UN = 8;
+#pragma unroll 1
+      for (int it0 = 0; it0 < 32; it0 += UN)
         {
-        const uint32_t r = ci / (uint32_t)ROWV, v = ci - r * (uint32_t)ROWV;
-        const uint4 val = *reinterpret_cast<const uint4*>(stagebuf + (size_t)r * ROWW + 4u * v);
-        __stcs(reinterpret_cast<uint4*>(tile_out + (size_t)r * row_bytes + 16u * v), val);
+        uint32_t v[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) v[u] = from[(size_t)(it0 + u) * R * ROWW];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) __stcs(reinterpret_cast<uint32_t*>(to + (size_t)(it0 + u) * R * row_bytes), v[u]);
         }
       }
     else
@@ -608,22 +720,30 @@ __device__ __forceinline__ void warp_copy_global(uint8_t* __restrict__ dst, cons
   if (done + lane < n) dst[done + lane] = __ldcg(src + done + lane);
   }
 
-template <typename W, int NCOMP, int R, int SB>
-__global__ void __launch_bounds__(NCOMP * R * 32, 15 / (NCOMP * R))
+#ifndef TB200_FPC_ENC_WARPS
+#define TB200_FPC_ENC_WARPS 15      // resident warps per SM the register allocation aims at
+#endif
+template <typename W, int NCOMP, int R, int SB, int EXP>
+#ifdef TB200_FPC_ENC_MAXNREG
+__global__ void __maxnreg__(TB200_FPC_ENC_MAXNREG)
+#else
+__global__ void __launch_bounds__(NCOMP * R * 32, TB200_FPC_ENC_WARPS / (NCOMP * R))
+#endif
 fpc_encode_lanes_kernel(const FpcEncodeArgs a)
   {
+  const int e1 = EXP ? (EXP >> 8) : a.e1, e2 = EXP ? (EXP & 255) : a.e2;
   using TR = FpcTraits<W>;
-  using WIN = FpcWindow<W, SB>;
+  using WIN = FpcEncWindow<W, SB>;
   constexpr int NWARPS = NCOMP * R;
   constexpr int NTHREADS = NWARPS * 32;                   // == chunks per tile
   constexpr int WV = WIN::VECS;                           // 16-byte vectors per lane window
   constexpr int WPV = sizeof(W) / 4;
-  constexpr int ROWV = SB * NCOMP * WPV / 4;
-  constexpr int ROWW = SB * NCOMP * WPV + 4;
+  constexpr int ROWV = SB * NCOMP * WPV / 4;              // 16-byte vectors per staged row
+  constexpr int ROWW = fpc_stage_row_words_enc(SB, NCOMP, sizeof(W));   // rows stay 16-byte aligned (16-byte cp.async)
   static_assert((SB * NCOMP * WPV) % 4 == 0, "staged rows must be whole vectors");
   static_assert(SB % TR::GROUP == 0, "sub-blocks hold whole groups");
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const uint32_t nt1 = 1u << a.e1, nt2 = 1u << a.e2;
+  const uint32_t nt1 = 1u << e1, nt2 = 1u << e2;
   uint32_t* win = reinterpret_cast<uint32_t*>(smem_raw);                               // [NWARPS][32][WV*4]
   uint32_t* stagebuf = win + (size_t)NWARPS * 32 * WV * 4;                             // [32*R][ROWW]
   W* tables = reinterpret_cast<W*>(stagebuf + (size_t)32 * R * ROWW);                  // [NWARPS][nt1+nt2][32]
@@ -637,7 +757,7 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
   const uint32_t c = warp % NCOMP, rgrp = warp / NCOMP;
   const uint32_t klocal = rgrp * 32 + lane;
   const uint32_t S = 1u << a.log2S;
-  const uint32_t h2 = (uint32_t)a.e2 >> 1, m2 = nt2 - 1;
+  const uint32_t h2 = (uint32_t)e2 >> 1, m2 = nt2 - 1;
   W* T1 = tables + (size_t)warp * (nt1 + nt2) * 32 + lane;
   W* T2 = T1 + (size_t)nt1 * 32;
   uint32_t* wrow = win + ((size_t)warp * 32 + lane) * WV * 4;
@@ -741,11 +861,11 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
             const W v = *reinterpret_cast<const W*>(srow + (size_t)idx * NCOMP * WPV);
             const W x1 = v ^ pred1, x2 = v ^ pred2;
             T1[(size_t)c1 * 32] = v;
-            c1 = (uint32_t)(v >> (TR::BITS - a.e1));
+            c1 = (uint32_t)(v >> (TR::BITS - e1));
             pred1 = T1[(size_t)c1 * 32];
             const W st = v - last;
             T2[(size_t)c2 * 32] = st;
-            c2 = ((c2 << h2) ^ (uint32_t)(st >> (TR::BITS - a.e2))) & m2;
+            c2 = ((c2 << h2) ^ (uint32_t)(st >> (TR::BITS - e2))) & m2;
             pred2 = v + T2[(size_t)c2 * 32];
             last = v;
             // code selection, fpc.c:146-189 / :635-782

@@ -504,7 +504,8 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
 
 // Assembly: chunk g's block sits at scratch + g*slot with its size in sizes[g]; tiles of
 // LZ4_ASM_TILE chunks take their base from a look-back over tile totals (all known up front, so
-// no waiting), then the CTA's 8 warps copy the tile's blocks to their final offsets.
+// no waiting), then the CTA copies the tile's blocks to their final offsets, the bytes spread
+// evenly over its threads.
 constexpr int LZ4_ASM_THREADS = 256;
 constexpr int LZ4_ASM_TILE = 128;
 
@@ -551,69 +552,82 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
       }
     }
   __syncthreads();
-  for (uint32_t c = warp; c < LZ4_ASM_TILE && g0 + c < nchunks; c += LZ4_ASM_THREADS / 32)
+  // The tile's output is one contiguous byte range; its 16-byte destination vectors are dealt to the
+  // threads round robin, whatever chunk they belong to (blocks of an incompressible plane are 200
+  // times larger than those of a constant one: a chunk-per-warp split leaves most warps idle).
+  // A vector that lies inside one chunk is built from the two aligned source vectors around it;
+  // vectors on a chunk boundary or at the ragged ends of the tile are copied byte by byte.
+  const uint32_t nloc = (uint32_t)((nchunks - g0 < (uint64_t)LZ4_ASM_TILE) ? (nchunks - g0) : (uint64_t)LZ4_ASM_TILE);
+  uint8_t* D = a.payload + sh_base;
+  const uint32_t lead = (uint32_t)reinterpret_cast<uintptr_t>(D) & 15u;          // tile byte t lives in vector (t + lead) / 16
+  uint8_t* D16 = D - lead;
+  const uint32_t nvec = (tsum + lead + 15u) >> 4;
+  const uint8_t* sbase = a.scratch + g0 * a.slot;
+  uint32_t c = 0;                                                                  // chunk of the previous vector: positions only grow
+  constexpr int UN = 4;
+  for (uint32_t j0 = threadIdx.x; j0 < nvec; j0 += LZ4_ASM_THREADS * UN)
     {
-    const uint32_t nbytes = sh_sz[c];
-    const uint8_t* src = a.scratch + (g0 + c) * a.slot;                  // 16-byte aligned
-    uint8_t* dst = a.payload + sh_base + sh_off[c];
-    uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
-    if (head > nbytes) head = nbytes;
-    if (lane < head) dst[lane] = src[lane];
-    const uint32_t nvec = (nbytes - head) >> 4;
-    uint4* dv = reinterpret_cast<uint4*>(dst + head);
-    if ((head & 3u) == 0)
-      { // source words line up with the destination vectors
-      const uint32_t* sw = reinterpret_cast<const uint32_t*>(src + head);
-      const unsigned sh = 0; (void)sh;
-      constexpr int UN = 4;
-      for (uint32_t i0 = 0; i0 < nvec; i0 += 32 * UN)
-        {
-        uint32_t w[UN][4];
+    uint4 va[UN], vb[UN];
+    uint32_t mis[UN], kind[UN], cu[UN];                                            // kind: 0 nothing, 1 vector path, 2 byte path
 #pragma unroll
-        for (int u = 0; u < UN; ++u)
-          {
-          const uint32_t i = i0 + lane + 32 * u;
-          if (i < nvec) { const uint32_t* q = sw + 4 * i; w[u][0] = __ldcs(q); w[u][1] = __ldcs(q + 1); w[u][2] = __ldcs(q + 2); w[u][3] = __ldcs(q + 3); }
-          }
-#pragma unroll
-        for (int u = 0; u < UN; ++u)
-          {
-          const uint32_t i = i0 + lane + 32 * u;
-          if (i < nvec) dv[i] = make_uint4(w[u][0], w[u][1], w[u][2], w[u][3]);
-          }
-        }
-      }
-    else
+    for (int u = 0; u < UN; ++u)
       {
-      const uint32_t* sw = reinterpret_cast<const uint32_t*>(src + (head & ~3u));
-      const unsigned sh = (head & 3u) * 8u;
-      constexpr int UN = 4;
-      for (uint32_t i0 = 0; i0 < nvec; i0 += 32 * UN)
+      const uint32_t j = j0 + (uint32_t)u * LZ4_ASM_THREADS;
+      kind[u] = 0; mis[u] = 0; cu[u] = 0;
+      if (j >= nvec) continue;
+      const int32_t t0 = (int32_t)(16u * j) - (int32_t)lead;                      // tile byte of the vector's first byte
+      const uint32_t tf = t0 < 0 ? 0u : (uint32_t)t0;
+      while (c + 1 < nloc && tf >= sh_off[c] + sh_sz[c]) ++c;
+      cu[u] = c;
+      const uint32_t lo = sh_off[c];
+      if (t0 >= (int32_t)lo && (uint32_t)t0 + 16u <= lo + sh_sz[c])
         {
-        uint32_t w[UN][5];
+        const uint8_t* src = sbase + (size_t)c * a.slot + ((uint32_t)t0 - lo);     // slots are 16-byte aligned, one spare vector behind every block
+        mis[u] = (uint32_t)reinterpret_cast<uintptr_t>(src) & 15u;
+        const uint4* s16 = reinterpret_cast<const uint4*>(src - mis[u]);
+        va[u] = __ldcs(s16); vb[u] = __ldcs(s16 + 1);
+        kind[u] = 1;
+        }
+      else kind[u] = 2;
+      }
 #pragma unroll
-        for (int u = 0; u < UN; ++u)
+    for (int u = 0; u < UN; ++u)
+      {
+      const uint32_t j = j0 + (uint32_t)u * LZ4_ASM_THREADS;
+      if (kind[u] == 1)
+        {
+        const uint32_t w[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+        const unsigned sh = (mis[u] & 3u) * 8u;
+        uint4 o;
+        switch (mis[u] >> 2)
           {
-          const uint32_t i = i0 + lane + 32 * u;
-          if (i < nvec)
-            {
-            const uint32_t* q = sw + 4 * i;
+          case 0: o = make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh)); break;
+          case 1: o = make_uint4(__funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh)); break;
+          case 2: o = make_uint4(__funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh)); break;
+          default: o = make_uint4(__funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh), __funnelshift_r(w[6], w[7], sh)); break;
+          }
+        *reinterpret_cast<uint4*>(D16 + 16u * (size_t)j) = o;
+        }
+      else if (kind[u] == 2)
+        { // all sixteen source bytes are requested before any is stored (one memory latency, not sixteen)
+        uint32_t cc = cu[u];
+        uint32_t val[16];
+        unsigned okm = 0;
 #pragma unroll
-            for (int j = 0; j < 5; ++j) w[u][j] = __ldcs(q + j);
-            }
+        for (uint32_t b = 0; b < 16u; ++b)
+          {
+          const int32_t t = (int32_t)(16u * j + b) - (int32_t)lead;
+          val[b] = 0;
+          if (t < 0 || (uint32_t)t >= tsum) continue;
+          while (cc + 1 < nloc && (uint32_t)t >= sh_off[cc] + sh_sz[cc]) ++cc;
+          val[b] = __ldcs(sbase + (size_t)cc * a.slot + ((uint32_t)t - sh_off[cc]));
+          okm |= 1u << b;
           }
 #pragma unroll
-        for (int u = 0; u < UN; ++u)
-          {
-          const uint32_t i = i0 + lane + 32 * u;
-          if (i < nvec)
-            dv[i] = make_uint4(__funnelshift_r(w[u][0], w[u][1], sh), __funnelshift_r(w[u][1], w[u][2], sh),
-                               __funnelshift_r(w[u][2], w[u][3], sh), __funnelshift_r(w[u][3], w[u][4], sh));
-          }
+        for (uint32_t b = 0; b < 16u; ++b)
+          if (okm & (1u << b)) D16[16u * (size_t)j + b] = (uint8_t)val[b];
         }
       }
-    const uint32_t done = head + (nvec << 4);
-    if (done + lane < nbytes) dst[done + lane] = src[done + lane];
     }
   }
 
