@@ -36,6 +36,27 @@ __device__ __forceinline__ uint4 smem_read128(const uint8_t* base, uint32_t pos)
   return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
   }
 
+// The same for positions whose low four bits are equal in every lane of the warp (lanes 16 bytes
+// apart) in a 16-byte aligned buffer: two aligned 16-byte reads - no bank conflicts, where the five
+// word reads above collide four ways - and the byte shift resolved by a warp-uniform branch.  Up to
+// 15 bytes past the vector must be readable.
+__device__ __forceinline__ uint4 smem_read128u(const uint8_t* base, uint32_t pos)
+  {
+  const uint4* v = reinterpret_cast<const uint4*>(base + (pos & ~15u));
+  const uint4 a = v[0];
+  const uint32_t m = pos & 15u;
+  if (m == 0) return a;
+  const uint4 b = v[1];
+  const unsigned sh = (m & 3u) * 8u;
+  switch (m >> 2)
+    {
+    case 0: return make_uint4(__funnelshift_r(a.x, a.y, sh), __funnelshift_r(a.y, a.z, sh), __funnelshift_r(a.z, a.w, sh), __funnelshift_r(a.w, b.x, sh));
+    case 1: return make_uint4(__funnelshift_r(a.y, a.z, sh), __funnelshift_r(a.z, a.w, sh), __funnelshift_r(a.w, b.x, sh), __funnelshift_r(b.x, b.y, sh));
+    case 2: return make_uint4(__funnelshift_r(a.z, a.w, sh), __funnelshift_r(a.w, b.x, sh), __funnelshift_r(b.x, b.y, sh), __funnelshift_r(b.y, b.z, sh));
+    default: return make_uint4(__funnelshift_r(a.w, b.x, sh), __funnelshift_r(b.x, b.y, sh), __funnelshift_r(b.y, b.z, sh), __funnelshift_r(b.z, b.w, sh));
+    }
+  }
+
 // warp copy of n literal bytes src[s..s+n) (shared memory) to dst (any alignment, any space);
 // long runs move as 16-byte vectors (512 bytes per warp instruction), four in flight per lane
 template <typename DstPtr>
@@ -59,7 +80,7 @@ __device__ __forceinline__ void lz4_copy_from_smem(DstPtr dst, const uint8_t* sr
     for (int u = 0; u < UN; ++u)
       {
       const uint32_t i = i0 + lane + 32 * u;
-      if (i < nv) v[u] = smem_read128(src, s + head + 16u * i);
+      if (i < nv) v[u] = smem_read128u(src, s + head + 16u * i);
       }
 #pragma unroll
     for (int u = 0; u < UN; ++u)
@@ -96,7 +117,7 @@ __device__ __forceinline__ uint32_t lz4_emit(DstPtr dst, uint32_t op, const uint
   return op;
   }
 
-constexpr uint32_t LZ4_SRC_PAD = 560;    // zeroed bytes the compressor may read past the block end (512-byte match extension steps)
+constexpr uint32_t LZ4_SRC_PAD = 576;    // zeroed bytes the compressor may read past the block end (512-byte match extension steps)
 
 // Compresses src[0..n) (shared memory, LZ4_SRC_PAD zero bytes readable past n) into dst.
 // `table` = (1 << HLOG) u16 entries of shared memory private to the warp.  n <= 65535.
@@ -186,7 +207,7 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
           len += 128;
           while (len < maxlen)
             {
-            const uint4 va = smem_read128(src, mq + len + 16 * lane), vb = smem_read128(src, mc + len + 16 * lane);
+            const uint4 va = smem_read128u(src, mq + len + 16 * lane), vb = smem_read128u(src, mc + len + 16 * lane);
             const uint32_t x0 = va.x ^ vb.x, x1 = va.y ^ vb.y, x2 = va.z ^ vb.z, x3 = va.w ^ vb.w;
             const unsigned nw = __ballot_sync(FULL, (x0 | x1 | x2 | x3) != 0);
             if (nw == 0) { len += 512; continue; }
@@ -377,6 +398,7 @@ struct Lz4EncodeArgs
   uint32_t slot;           // bytes per scratch slot (>= lz4_block_bound(B), multiple of 16)
   uint64_t* desc;          // look-back descriptors of the assemble kernel, zeroed
   uint32_t* ticket;        // chunk ticket, zeroed
+  unsigned long long* dbg; // phase-cycle counters by plane (experiments; nullptr in production)
   };
 
 constexpr int LZ4_HLOG = 10;     // default: 1024 u16 entries = 2 KiB per warp (12 resident warps per SM with 16 KiB blocks)
@@ -402,6 +424,9 @@ __device__ __forceinline__ uint32_t plane_bytes(const uint4 v, uint32_t p)
   return ((a >> (8 * (p & 3))) & 0xffu) | (((b >> (8 * (p & 3))) & 0xffu) << 8);
   }
 
+#ifndef TB200_LZ4_ENC_LOAD_UN
+#define TB200_LZ4_ENC_LOAD_UN 16     // 16-byte loads in flight per lane while a range is split into planes
+#endif
 template <int WB, int HLOG>
 __global__ void __launch_bounds__(Lz4Cta<WB>::WARPS * 32)
 lz4_encode_kernel(const Lz4EncodeArgs a)
@@ -433,6 +458,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
       }
     const uint64_t k = g / WB;
     const uint32_t p = (uint32_t)(g % WB);
+    long long t_ph = a.dbg ? clock64() : 0;
     const uint64_t lo = k << a.log2B;
     const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
 
@@ -441,7 +467,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
     if ((reinterpret_cast<uintptr_t>(gin) & 15u) == 0)
       {
       constexpr int EPV = 16 / WB;                                   // elements per 16-byte vector
-      constexpr int UN = 8;
+      constexpr int UN = TB200_LZ4_ENC_LOAD_UN;
       const uint32_t nvec = cnt / EPV;
       const uint4* g4 = reinterpret_cast<const uint4*>(gin);
       const uint32_t nfull = nvec / (32 * UN);                       // whole batches of UN vectors per lane
@@ -453,33 +479,23 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
         else if (WB == 2) reinterpret_cast<uint2*>(buf)[i] = make_uint2(__byte_perm(v.x, v.y, sel2), __byte_perm(v.z, v.w, sel2));
         else reinterpret_cast<uint16_t*>(buf)[i] = (uint16_t)plane_bytes<8>(v, p);
         };
-      // two register sets used alternately (no copies between them): while one batch is split,
-      // the loads of the next one are in flight
-      uint4 ra[UN], rb[UN];
+      // rolling window of UN vectors per lane: as soon as a vector has been split its register takes the
+      // load of the same position in the next batch, so UN loads per lane stay in flight throughout
+      uint4 r[UN];
       if (nfull)
         {
 #pragma unroll
-        for (int u = 0; u < UN; ++u) ra[u] = __ldg(g4 + lane + 32 * u);
+        for (int u = 0; u < UN; ++u) r[u] = __ldg(g4 + lane + 32 * u);
         }
-      uint32_t bidx = 0;
-      while (bidx < nfull)
+      for (uint32_t bidx = 0; bidx < nfull; ++bidx)
         {
-        if (bidx + 1 < nfull)
+        const bool more = bidx + 1 < nfull;
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
           {
-#pragma unroll
-          for (int u = 0; u < UN; ++u) rb[u] = __ldg(g4 + (bidx + 1) * 32 * UN + lane + 32 * u);
+          put(r[u], bidx * 32 * UN + lane + 32 * u);
+          if (more) r[u] = __ldg(g4 + (bidx + 1) * 32 * UN + lane + 32 * u);
           }
-#pragma unroll
-        for (int u = 0; u < UN; ++u) put(ra[u], bidx * 32 * UN + lane + 32 * u);
-        if (++bidx >= nfull) break;
-        if (bidx + 1 < nfull)
-          {
-#pragma unroll
-          for (int u = 0; u < UN; ++u) ra[u] = __ldg(g4 + (bidx + 1) * 32 * UN + lane + 32 * u);
-          }
-#pragma unroll
-        for (int u = 0; u < UN; ++u) put(rb[u], bidx * 32 * UN + lane + 32 * u);
-        ++bidx;
         }
       for (uint32_t i = nfull * 32 * UN + lane; i < nvec; i += 32) put(__ldg(g4 + i), i);
       for (uint32_t i = nvec * EPV + lane; i < cnt; i += 32) buf[i] = gin[(size_t)i * WB + p];
@@ -490,8 +506,10 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
     for (uint32_t i = lane; i < LZ4_SRC_PAD; i += 32) buf[cnt + i] = 0;
     __syncwarp();
 
+    if (a.dbg && lane == 0) { const long long t2 = clock64(); atomicAdd(a.dbg + (p & 7), (unsigned long long)(t2 - t_ph)); t_ph = t2; }
     // 2. compress into this chunk's slot
     const uint32_t nbytes = lz4_compress_warp<HLOG>(buf, cnt, a.scratch + g * a.slot, table);
+    if (a.dbg && lane == 0) { const long long t2 = clock64(); atomicAdd(a.dbg + 8 + (p & 7), (unsigned long long)(t2 - t_ph)); }
     if (lane == 0)
       {
       uint8_t* sz = a.sizes + 2 * g;
@@ -696,7 +714,7 @@ __device__ __forceinline__ void lz4_smem_move(uint8_t* buf, uint32_t dst, uint32
     for (int u = 0; u < UN; ++u)
       {
       const uint32_t i = i0 + lane + 32 * u;
-      if (i < nv) v[u] = smem_read128(buf, s0 + 16u * i);
+      if (i < nv) v[u] = smem_read128u(buf, s0 + 16u * i);
       }
     if (FORWARD_OVERLAP) __syncwarp();
 #pragma unroll
@@ -718,6 +736,9 @@ __device__ __forceinline__ void lz4_smem_move(uint8_t* buf, uint32_t dst, uint32
 // ceil(2^32 / o) for o = 2..32: t mod o = t - o * umulhi(t, inv) is exact for t < 2^16.  Offset 1
 // would need 2^32; its entry is 0 and the result is masked to 0 (every index of a run is 0).
 __constant__ uint32_t c_lz4_inv[33] = { 0x00000000u, 0x00000000u, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2aaaaaabu, 0x24924925u, 0x20000000u, 0x1c71c71du, 0x1999999au, 0x1745d175u, 0x15555556u, 0x13b13b14u, 0x12492493u, 0x11111112u, 0x10000000u, 0x0f0f0f10u, 0x0e38e38fu, 0x0d79435fu, 0x0ccccccdu, 0x0c30c30du, 0x0ba2e8bbu, 0x0b21642du, 0x0aaaaaabu, 0x0a3d70a4u, 0x09d89d8au, 0x097b425fu, 0x0924924au, 0x08d3dcb1u, 0x08888889u, 0x08421085u, 0x08000000u };
+
+// S(offset) = 32 - 32 mod Q, Q = offset / gcd(offset, 16): see lz4_match_warp
+__constant__ uint8_t c_lz4_stride[33] = { 32, 32, 32, 30, 32, 30, 30, 28, 32, 27, 30, 22, 30, 26, 28, 30, 32, 17, 27, 19, 30, 21, 22, 23, 30, 25, 26, 27, 28, 29, 30, 31, 32 };
 
 // One match, produced by the whole warp.  opm = output position of the match.  Exact: nothing is
 // written at or past opm + mlen (the next sequence's literals are already in place).
@@ -744,26 +765,14 @@ __device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint3
       uint32_t xa = (opm + 64u) & ~15u;                                  // aligned, inside the table: rewriting [xa, opm+64) is harmless
       const uint32_t nv = (end - xa) >> 4;
       const uint32_t t0 = xa - opm;
-      if (nv <= 64u)
-        { // up to 1 KiB: one or two vectors per lane, nothing computed that is not stored
-        if (lane < nv) *reinterpret_cast<uint4*>(buf + xa + 16u * lane) = smem_read128(buf, opm + modo(t0 + 16u * lane));
-        if (lane + 32u < nv) *reinterpret_cast<uint4*>(buf + xa + 16u * (lane + 32u)) = smem_read128(buf, opm + modo(t0 + 16u * (lane + 32u)));
-        }
-      else
+      // The aligned vectors of the match repeat every Q = offset / gcd(offset, 16) vectors, so a lane
+      // that strides by S = the largest multiple of Q not above 32 stores the SAME vector every time:
+      // one table read per lane, whatever the match length.
+      const uint32_t S = c_lz4_stride[offset];
+      if (lane < S)
         {
-        constexpr int UN = 4;
-        for (uint32_t i0 = 0; i0 < nv; i0 += 32 * UN)
-          {
-          uint4 v[UN];
-#pragma unroll
-          for (int u = 0; u < UN; ++u) v[u] = smem_read128(buf, opm + modo(t0 + 16u * (i0 + lane + 32 * u)));
-#pragma unroll
-          for (int u = 0; u < UN; ++u)
-            {
-            const uint32_t i = i0 + lane + 32 * u;
-            if (i < nv) *reinterpret_cast<uint4*>(buf + xa + 16u * i) = v[u];
-            }
-          }
+        const uint4 v = smem_read128(buf, opm + modo(t0 + 16u * lane));
+        for (uint32_t i = lane; i < nv; i += S) *reinterpret_cast<uint4*>(buf + xa + 16u * i) = v;
         }
       const uint32_t done = xa + (nv << 4);
       if (done + lane < end) buf[done + lane] = buf[opm + modo(done - opm + lane)];
