@@ -117,6 +117,30 @@ __device__ __forceinline__ uint32_t lz4_emit(DstPtr dst, uint32_t op, const uint
   return op;
   }
 
+// The block the matcher below produces for n >= 25 copies of byte v: one literal, a match at
+// offset 1 up to the last five bytes, five literals (lz4.c:189-196).  Returns its size.
+template <typename DstPtr>
+__device__ __forceinline__ uint32_t lz4_emit_run(DstPtr dst, uint32_t n, uint32_t v)
+  {
+  const unsigned lane = lane_id();
+  const uint32_t m = n - 10u;                           // match length n - 6, minus LZ4_MINMATCH
+  const uint32_t mext = (m - 15u) / 255u + 1u;          // length continuation bytes
+  const uint32_t total = 4u + mext + 6u;
+  for (uint32_t i = lane; i < total; i += 32)
+    {
+    uint32_t byte;
+    if (i == 0) byte = 0x1fu;                           // 1 literal, match length continued
+    else if (i == 1) byte = v;
+    else if (i == 2) byte = 1u;                         // offset 1, little-endian
+    else if (i == 3) byte = 0u;
+    else if (i < 4u + mext) byte = (i + 1u == 4u + mext) ? (m - 15u) % 255u : 255u;
+    else if (i == 4u + mext) byte = 0x50u;              // last sequence: 5 literals
+    else byte = v;
+    dst[i] = (uint8_t)byte;
+    }
+  return total;
+  }
+
 constexpr uint32_t LZ4_SRC_PAD = 576;    // zeroed bytes the compressor may read past the block end (512-byte match extension steps)
 
 // Compresses src[0..n) (shared memory, LZ4_SRC_PAD zero bytes readable past n) into dst.
@@ -125,8 +149,11 @@ constexpr uint32_t LZ4_SRC_PAD = 576;    // zeroed bytes the compressor may read
 // (lz4.c:879-909) the scan accelerates over data that does not match: after every 64 failed
 // attempts the distance between tested positions grows by one.
 template <int HLOG, typename DstPtr>
-__device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* table)
+__device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* table, unsigned long long* dbg = nullptr)
   {
+#define TB200_EPH(i) do { if (dbg) { const long long t__ = clock64(); acc_ph[i] += (uint32_t)(t__ - t_ph); t_ph = t__; } } while (0)
+  long long t_ph = dbg ? clock64() : 0;
+  uint32_t acc_ph[5] = {0, 0, 0, 0, 0};
   const unsigned lane = lane_id();
   const unsigned gt = lanemask_gt(), lt = lanemask_lt();
   uint32_t op = 0, anchor = 0;
@@ -176,8 +203,9 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
         if (lost) table[h] = (uint16_t)q;
         __syncwarp();
         }
-      if (mask == 0) { p += 32u * stride; attempts += 32; continue; }
+      if (mask == 0) { p += 32u * stride; attempts += 32; TB200_EPH(0); continue; }
       attempts = 0;
+      TB200_EPH(1);
       uint32_t mq = p + (uint32_t)f * stride;
       uint32_t mc = __shfl_sync(FULL, cand, f);
       // backward extension over bytes not yet emitted (lz4.c:947-950 does the same serially)
@@ -221,15 +249,20 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
           }
         }
       if (len > maxlen) len = maxlen;
+      TB200_EPH(2);
       op = lz4_emit(dst, op, src, anchor, mq - anchor, mq - mc, len);
       p = anchor = mq + len;
       // like lz4.c:1118, remember one position inside the match tail
       if (lane == 0 && p - 2 <= mflimit) table[(smem_read32(src, p - 2) * 2654435761u) >> (32 - HLOG)] = (uint16_t)(p - 2);
       __syncwarp();
+      TB200_EPH(3);
       }
     }
   op = lz4_emit(dst, op, src, anchor, n - anchor, 0, 0);
+  TB200_EPH(4);
+  if (dbg && lane == 0) for (int i = 0; i < 5; ++i) atomicAdd(dbg + i, (unsigned long long)acc_ph[i]);
   return op;
+#undef TB200_EPH
   }
 
 // copy `n` bytes inside the output buffer from distance `dist` >= n behind (non-overlapping)
@@ -376,11 +409,12 @@ __device__ __forceinline__ uint32_t lz4_decompress_warp(const uint8_t* __restric
 // transpose_aos_to_soa.c:84-147) fused with per-plane-block LZ4 compression and the assembly.
 //
 // Two kernels.  lz4_encode_kernel: every WARP is independent (no barrier, no ordering): persistent
-// warps pull chunks g = (range k, plane p), g = k*WB + p, from an atomic ticket;
+// warps pull ranges k of B elements from an atomic ticket and compress their planes p one after
+// the other (chunk g = k*WB + p):
 //   1. the warp reads the range's AoS elements with coalesced 16-byte loads and keeps byte p of
-//      every element (consecutive tickets = the planes of one range, taken at about the same
-//      time, so the re-reads are L1/L2 hits and DRAM sees the range once)
-//   2. it compresses its plane block into the chunk's own scratch slot and records the size.
+//      every element (the range comes from DRAM once; the passes for the other planes hit L2);
+//      planes that the first pass found to be one repeated byte are not extracted at all
+//   2. it compresses the plane block into the chunk's own scratch slot and records the size.
 // lz4_assemble_kernel: block scan of the sizes + decoupled look-back over tiles of 64 chunks,
 // then every block is copied to its final offset (only compressed bytes move twice).
 // ---------------------------------------------------------------------------------------------
@@ -438,85 +472,124 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
   uint8_t* buf = smem_raw + (size_t)warp * pstride;
   uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WARPS * pstride) + ((size_t)warp << HLOG);
-  const uint64_t nchunks = (uint64_t)a.nranges * WB;
 
-  // tickets are taken one chunk ahead so the next range can be pulled towards L2 while this
-  // chunk is being compressed
+  // A ticket is a RANGE of B elements; the warp compresses its WB planes one after the other.  The
+  // pass that extracts the first plane also notes in which bits the elements of the range differ at
+  // all: a plane none of whose bits ever changes (the upper planes of index data, mostly) is one
+  // repeated byte and gets its encoding written without being extracted or searched.
+  // Tickets are taken one range ahead so the next range can be pulled towards L2 meanwhile.
   uint32_t t32 = 0;
   if (lane == 0) t32 = atomicAdd(a.ticket, 1u);
-  uint64_t g = __shfl_sync(FULL, t32, 0);
-  while (g < nchunks)
+  uint64_t k = __shfl_sync(FULL, t32, 0);
+  while (k < a.nranges)
     {
     if (lane == 0) t32 = atomicAdd(a.ticket, 1u);
-    const uint64_t gnext = __shfl_sync(FULL, t32, 0);
-    if (gnext < nchunks)
-      {
-      const uint8_t* nx = reinterpret_cast<const uint8_t*>(a.in) + ((gnext / WB) << a.log2B) * WB;
-      const uint64_t lim = a.n * WB;
-      for (uint32_t o = lane * 128u; o < B * WB; o += 32u * 128u)
-        if (((gnext / WB) << a.log2B) * WB + o < lim) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + o));
-      }
-    const uint64_t k = g / WB;
-    const uint32_t p = (uint32_t)(g % WB);
-    long long t_ph = a.dbg ? clock64() : 0;
+    const uint64_t knext = __shfl_sync(FULL, t32, 0);
     const uint64_t lo = k << a.log2B;
     const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
-
-    // 1. plane p of range k -> buf (loads of the next batch are in flight while this one is split)
     const uint8_t* gin = reinterpret_cast<const uint8_t*>(a.in) + lo * WB;
-    if ((reinterpret_cast<uintptr_t>(gin) & 15u) == 0)
-      {
-      constexpr int EPV = 16 / WB;                                   // elements per 16-byte vector
-      constexpr int UN = TB200_LZ4_ENC_LOAD_UN;
-      const uint32_t nvec = cnt / EPV;
-      const uint4* g4 = reinterpret_cast<const uint4*>(gin);
-      const uint32_t nfull = nvec / (32 * UN);                       // whole batches of UN vectors per lane
-      const uint32_t sel2 = p | ((2u + p) << 4) | ((4u + p) << 8) | ((6u + p) << 12);
-      auto put = [&](const uint4 v, uint32_t i)
-        { // byte p of every element of vector i -> plane buffer
-        if (WB == 1) reinterpret_cast<uint4*>(buf)[i] = v;
-        else if (WB == 4) reinterpret_cast<uint32_t*>(buf)[i] = plane_bytes<4>(v, p);
-        else if (WB == 2) reinterpret_cast<uint2*>(buf)[i] = make_uint2(__byte_perm(v.x, v.y, sel2), __byte_perm(v.z, v.w, sel2));
-        else reinterpret_cast<uint16_t*>(buf)[i] = (uint16_t)plane_bytes<8>(v, p);
-        };
-      // rolling window of UN vectors per lane: as soon as a vector has been split its register takes the
-      // load of the same position in the next batch, so UN loads per lane stay in flight throughout
-      uint4 r[UN];
-      if (nfull)
-        {
-#pragma unroll
-        for (int u = 0; u < UN; ++u) r[u] = __ldg(g4 + lane + 32 * u);
-        }
-      for (uint32_t bidx = 0; bidx < nfull; ++bidx)
-        {
-        const bool more = bidx + 1 < nfull;
-#pragma unroll
-        for (int u = 0; u < UN; ++u)
-          {
-          put(r[u], bidx * 32 * UN + lane + 32 * u);
-          if (more) r[u] = __ldg(g4 + (bidx + 1) * 32 * UN + lane + 32 * u);
-          }
-        }
-      for (uint32_t i = nfull * 32 * UN + lane; i < nvec; i += 32) put(__ldg(g4 + i), i);
-      for (uint32_t i = nvec * EPV + lane; i < cnt; i += 32) buf[i] = gin[(size_t)i * WB + p];
-      }
-    else
-      for (uint32_t i = lane; i < cnt; i += 32) buf[i] = gin[(size_t)i * WB + p];
-    // zero the read-ahead pad: the compressor compares up to LZ4_SRC_PAD bytes past cnt
-    for (uint32_t i = lane; i < LZ4_SRC_PAD; i += 32) buf[cnt + i] = 0;
-    __syncwarp();
+    const bool aligned = (reinterpret_cast<uintptr_t>(gin) & 15u) == 0;
 
-    if (a.dbg && lane == 0) { const long long t2 = clock64(); atomicAdd(a.dbg + (p & 7), (unsigned long long)(t2 - t_ph)); t_ph = t2; }
-    // 2. compress into this chunk's slot
-    const uint32_t nbytes = lz4_compress_warp<HLOG>(buf, cnt, a.scratch + g * a.slot, table);
-    if (a.dbg && lane == 0) { const long long t2 = clock64(); atomicAdd(a.dbg + 8 + (p & 7), (unsigned long long)(t2 - t_ph)); }
-    if (lane == 0)
+    uint32_t diff_lo = 0xffffffffu, diff_hi = 0xffffffffu;            // bits that differ somewhere in the range (bytes = planes); all set = unknown
+    uint32_t e0_lo = 0, e0_hi = 0;                                     // the range's first element
+    for (uint32_t p = 0; p < (uint32_t)WB; ++p)
       {
-      uint8_t* sz = a.sizes + 2 * g;
-      sz[0] = (uint8_t)nbytes; sz[1] = (uint8_t)(nbytes >> 8);
+      const uint64_t g = k * WB + p;
+      if (p == (uint32_t)WB - 1u && knext < a.nranges)
+        { // the next range -> L2, a few microseconds before its first pass (earlier and it is evicted again)
+        const uint8_t* nx = reinterpret_cast<const uint8_t*>(a.in) + (knext << a.log2B) * WB;
+        const uint64_t lim = a.n * WB;
+        for (uint32_t o = lane * 128u; o < B * WB; o += 32u * 128u)
+          if ((knext << a.log2B) * WB + o < lim) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + o));
+        }
+      long long t_ph = a.dbg ? clock64() : 0;
+      uint32_t nbytes;
+      const uint32_t pdiff = ((p < 4 ? diff_lo : diff_hi) >> (8 * (p & 3))) & 0xffu;
+      if (pdiff == 0)
+        nbytes = lz4_emit_run(a.scratch + g * a.slot, cnt, ((p < 4 ? e0_lo : e0_hi) >> (8 * (p & 3))) & 0xffu);
+      else
+        {
+        // 1. plane p of the range -> buf
+        if (aligned)
+          {
+          constexpr int EPV = 16 / WB;                                   // elements per 16-byte vector
+          constexpr int UN = TB200_LZ4_ENC_LOAD_UN;
+          const uint32_t nvec = cnt / EPV;
+          const uint4* g4 = reinterpret_cast<const uint4*>(gin);
+          const uint32_t nfull = nvec / (32 * UN);                       // whole batches of UN vectors per lane
+          const uint32_t sel2 = p | ((2u + p) << 4) | ((4u + p) << 8) | ((6u + p) << 12);
+          // first pass over a complete range: collect the differing bits of all planes
+          const bool survey = p == 0 && WB > 1 && cnt == B && nfull * 32 * UN == nvec;
+          const bool SURVEY = survey;
+            {
+            uint32_t r_lo = 0, r_hi = 0, d_lo = 0, d_hi = 0;               // reference element (this lane's first), differences to it
+            auto put = [&](const uint4 v, uint32_t i)
+              { // byte p of every element of vector i -> plane buffer
+              if (WB == 1) reinterpret_cast<uint4*>(buf)[i] = v;
+              else if (WB == 4) reinterpret_cast<uint32_t*>(buf)[i] = plane_bytes<4>(v, p);
+              else if (WB == 2) reinterpret_cast<uint2*>(buf)[i] = make_uint2(__byte_perm(v.x, v.y, sel2), __byte_perm(v.z, v.w, sel2));
+              else reinterpret_cast<uint16_t*>(buf)[i] = (uint16_t)plane_bytes<8>(v, p);
+              if (SURVEY)
+                {
+                if (WB == 8) { d_lo |= (v.x ^ r_lo) | (v.z ^ r_lo); d_hi |= (v.y ^ r_hi) | (v.w ^ r_hi); }
+                else d_lo |= (v.x ^ r_lo) | (v.y ^ r_lo) | (v.z ^ r_lo) | (v.w ^ r_lo);
+                }
+              };
+            // rolling window of UN vectors per lane: as soon as a vector has been split its register takes the
+            // load of the same position in the next batch, so UN loads per lane stay in flight throughout
+            uint4 r[UN];
+            if (nfull)
+              {
+#pragma unroll
+              for (int u = 0; u < UN; ++u) r[u] = __ldg(g4 + lane + 32 * u);
+              if (SURVEY)
+                { // 2-byte elements: compare whole words against the first element in both halves
+                r_lo = WB == 2 ? __byte_perm(r[0].x, 0u, 0x1010) : r[0].x;
+                r_hi = r[0].y;
+                }
+              }
+            for (uint32_t bidx = 0; bidx < nfull; ++bidx)
+              {
+              const bool more = bidx + 1 < nfull;
+#pragma unroll
+              for (int u = 0; u < UN; ++u)
+                {
+                put(r[u], bidx * 32 * UN + lane + 32 * u);
+                if (more) r[u] = __ldg(g4 + (bidx + 1) * 32 * UN + lane + 32 * u);
+                }
+              }
+            for (uint32_t i = nfull * 32 * UN + lane; i < nvec; i += 32) put(__ldg(g4 + i), i);
+            for (uint32_t i = nvec * EPV + lane; i < cnt; i += 32) buf[i] = gin[(size_t)i * WB + p];
+            if (SURVEY)
+              { // differences inside the lanes, plus between the lanes' reference elements
+              e0_lo = __shfl_sync(FULL, r_lo, 0); e0_hi = __shfl_sync(FULL, r_hi, 0);
+              d_lo |= r_lo ^ e0_lo; d_hi |= r_hi ^ e0_hi;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) { d_lo |= __shfl_xor_sync(FULL, d_lo, o); d_hi |= __shfl_xor_sync(FULL, d_hi, o); }
+              if (WB == 2) d_lo |= d_lo >> 16;                             // both halves of a word hold an element
+              diff_lo = d_lo; diff_hi = d_hi;
+              }
+            }
+          }
+        else
+          for (uint32_t i = lane; i < cnt; i += 32) buf[i] = gin[(size_t)i * WB + p];
+        // zero the read-ahead pad: the compressor compares up to LZ4_SRC_PAD bytes past cnt
+        for (uint32_t i = lane; i < LZ4_SRC_PAD; i += 32) buf[cnt + i] = 0;
+        __syncwarp();
+        if (a.dbg && lane == 0) { const long long t2 = clock64(); atomicAdd(a.dbg + (p & 7), (unsigned long long)(t2 - t_ph)); t_ph = t2; }
+
+        // 2. compress into this chunk's slot
+        nbytes = lz4_compress_warp<HLOG>(buf, cnt, a.scratch + g * a.slot, table, a.dbg ? a.dbg + 16 + 8 * (p & 7) : nullptr);
+        }
+      if (a.dbg && lane == 0) { const long long t2 = clock64(); atomicAdd(a.dbg + 8 + (p & 7), (unsigned long long)(t2 - t_ph)); }
+      if (lane == 0)
+        {
+        uint8_t* sz = a.sizes + 2 * g;
+        sz[0] = (uint8_t)nbytes; sz[1] = (uint8_t)(nbytes >> 8);
+        }
+      __syncwarp();
       }
-    __syncwarp();
-    g = gnext;
+    k = knext;
     }
   }
 
@@ -740,17 +813,38 @@ __constant__ uint32_t c_lz4_inv[33] = { 0x00000000u, 0x00000000u, 0x80000000u, 0
 // S(offset) = 32 - 32 mod Q, Q = offset / gcd(offset, 16): see lz4_match_warp
 __constant__ uint8_t c_lz4_stride[33] = { 32, 32, 32, 30, 32, 30, 30, 28, 32, 27, 30, 22, 30, 26, 28, 30, 32, 17, 27, 19, 30, 21, 22, 23, 30, 25, 26, 27, 28, 29, 30, 31, 32 };
 
+// Rest of a short-period match (offset <= 32 < mlen) once its first 64 bytes are in place: they
+// serve as a look-up table - the 16 bytes at any later position x are the 16 bytes at
+// opm + (x - opm) mod offset - so the remainder is produced with independent unaligned 16-byte
+// reads and aligned stores.  The aligned vectors repeat every Q = offset / gcd(offset, 16)
+// vectors, so a lane that strides by S = the largest multiple of Q not above 32 stores the SAME
+// vector every time: one table read per lane, whatever the match length.  Exact: nothing is written
+// at or past opm + mlen.
+template <typename Mod>
+__device__ __forceinline__ void lz4_period_rest(uint8_t* buf, uint32_t opm, uint32_t mlen, uint32_t S, Mod modo)
+  {
+  const unsigned lane = lane_id();
+  const uint32_t end = opm + mlen;
+  const uint32_t xa = (opm + 64u) & ~15u;                                // aligned, inside the table: rewriting [xa, opm+64) is harmless
+  const uint32_t nv = (end - xa) >> 4;
+  const uint32_t t0 = xa - opm;
+  if (lane < S)
+    {
+    const uint4 v = smem_read128(buf, opm + modo(t0 + 16u * lane));
+    for (uint32_t i = lane; i < nv; i += S) *reinterpret_cast<uint4*>(buf + xa + 16u * i) = v;
+    }
+  const uint32_t done = xa + (nv << 4);
+  if (done + lane < end) buf[done + lane] = buf[opm + modo(done - opm + lane)];
+  }
+
 // One match, produced by the whole warp.  opm = output position of the match.  Exact: nothing is
-// written at or past opm + mlen (the next sequence's literals are already in place).
+// written at or past opm + mlen.
 __device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint32_t offset, uint32_t mlen)
   {
   const unsigned lane = lane_id();
   if (offset <= 32u && mlen > offset)
     { // Short period (runs, interleaved index patterns).  The first 64 output bytes are written
-      // byte-wise (lane l: bytes l and l+32 of the pattern); they then serve as a look-up table:
-      // the 16 bytes at any later position x are the 16 bytes at opm + (x - opm) mod offset, so the
-      // rest of the match is produced with independent 16-byte reads and aligned stores, no further
-      // synchronisation and no dependence on the match length.
+      // byte-wise (lane l: bytes l and l+32 of the pattern), the rest by lz4_period_rest.
     const uint8_t* ms = buf + opm - offset;
     const uint32_t inv = c_lz4_inv[offset];
     const uint32_t keep = offset == 1u ? 0u : 0xffffffffu;
@@ -761,21 +855,7 @@ __device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint3
     if (mlen > 64u)
       {
       __syncwarp();
-      const uint32_t end = opm + mlen;
-      uint32_t xa = (opm + 64u) & ~15u;                                  // aligned, inside the table: rewriting [xa, opm+64) is harmless
-      const uint32_t nv = (end - xa) >> 4;
-      const uint32_t t0 = xa - opm;
-      // The aligned vectors of the match repeat every Q = offset / gcd(offset, 16) vectors, so a lane
-      // that strides by S = the largest multiple of Q not above 32 stores the SAME vector every time:
-      // one table read per lane, whatever the match length.
-      const uint32_t S = c_lz4_stride[offset];
-      if (lane < S)
-        {
-        const uint4 v = smem_read128(buf, opm + modo(t0 + 16u * lane));
-        for (uint32_t i = lane; i < nv; i += S) *reinterpret_cast<uint4*>(buf + xa + 16u * i) = v;
-        }
-      const uint32_t done = xa + (nv << 4);
-      if (done + lane < end) buf[done + lane] = buf[opm + modo(done - opm + lane)];
+      lz4_period_rest(buf, opm, mlen, c_lz4_stride[offset], modo);
       }
     }
   else if (offset >= mlen)
@@ -808,17 +888,23 @@ __device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip
   const unsigned lane = lane_id();
   uint32_t op = 0;
   if (ip >= iend) return 0xffffffffu;
+  // constants of the short-period generator, one offset per lane (lane l: offset l + 1); a shuffle
+  // is quicker than an indexed constant-memory read inside the loop
+  const uint32_t lane_inv = c_lz4_inv[lane + 1u], lane_stride = c_lz4_stride[lane + 1u];
+  // the token and the 31 bytes behind it in one read (32 readable bytes follow every block); the
+  // window of the NEXT sequence is requested as soon as its position is known, before the match of
+  // the current one is produced
+  uint32_t b = buf[ip + lane];
   for (;;)
     {
-    // the token and the 31 bytes behind it in one read (32 readable bytes follow every block)
-    const uint32_t b = buf[ip + lane];
     const uint32_t token = __shfl_sync(FULL, b, 0);
     uint32_t lit = token >> 4, ml = token & 15u, offset;
-    if (lit < 15u)
+    const bool short_lit = lit < 15u;
+    if (short_lit)
       {
       const uint32_t e = lit + 1u;                                  // index of the offset's low byte inside b
       if (ip + e > iend || op + lit > cap) return 0xffffffffu;
-      __syncwarp();
+      __syncwarp();                                                 // every lane holds its byte of b
       if (lane - 1u < lit) buf[op + lane - 1u] = (uint8_t)b;        // lanes 1..lit
       op += lit; ip += e;
       if (ip >= iend) break;                                        // last sequence has no match part
@@ -854,9 +940,38 @@ __device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip
       }
     const uint32_t mlen = ml + LZ4_MINMATCH;
     if (ip > iend || mlen > cap || offset == 0 || offset > op || op + mlen > cap) return 0xffffffffu;
-    __syncwarp();                                   // literals of this sequence are visible
-    lz4_match_warp(buf, op, offset, mlen);
+    // next window: unread input, which this sequence's output never reaches (in-place margin)
+    const uint32_t bnext = buf[ip + lane];
+    if (short_lit && offset <= 32u && mlen > offset)
+      { // Short-period match behind a short literal run (runs, interleaved index patterns).  The
+        // pattern is the `offset` bytes before the match: its last `lit` bytes are the literals, which
+        // this warp still holds in b (lanes 1..lit) - only older bytes are read from the buffer, so
+        // nothing here waits for the literal stores above.
+      const uint32_t inv = __shfl_sync(FULL, lane_inv, offset - 1u), S = __shfl_sync(FULL, lane_stride, offset - 1u);
+      const uint32_t keep = offset == 1u ? 0u : 0xffffffffu;
+      auto modo = [&](uint32_t t) { return (t - offset * __umulhi(t, inv)) & keep; };
+      const uint32_t r0 = modo(lane), r1 = modo(lane + 32u);
+      const int32_t first_lit = (int32_t)offset - (int32_t)lit;      // pattern index of the first literal (<= 0: literals only)
+      uint32_t q0 = __shfl_sync(FULL, b, (1u + r0 - (uint32_t)first_lit) & 31u);
+      uint32_t q1 = __shfl_sync(FULL, b, (1u + r1 - (uint32_t)first_lit) & 31u);
+      const uint8_t* ms = buf + op - offset;
+      if ((int32_t)r0 < first_lit) q0 = ms[r0];
+      if ((int32_t)r1 < first_lit) q1 = ms[r1];
+      if (lane < mlen) buf[op + lane] = (uint8_t)q0;
+      if (lane + 32u < mlen) buf[op + lane + 32u] = (uint8_t)q1;
+      if (mlen > 64u)
+        {
+        __syncwarp();
+        lz4_period_rest(buf, op, mlen, S, modo);
+        }
+      }
+    else
+      {
+      __syncwarp();                                 // literals of this sequence are visible
+      lz4_match_warp(buf, op, offset, mlen);
+      }
     op += mlen;
+    b = bnext;
     __syncwarp();
     }
   return op;
@@ -950,8 +1065,10 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
     const uint64_t base = sh_base[cur];
     const bool in_range = base + agg <= a.payload_bytes;
 
-    // 1. stage: block w goes to the tail of plane buffer w, at an offset congruent to its global
-    //    address modulo 16 so that the body moves as 16-byte cp.async copies
+    // 1. stage: every warp fetches its own block into the tail of its plane buffer, at an offset
+    //    congruent to the global address modulo 16 so that the body moves as 16-byte cp.async copies,
+    //    and waits for nothing else (the plane with the most sequences sets the pace of the tile and
+    //    is usually a few hundred bytes: it starts decoding one memory latency after the ticket)
     uint32_t my_ip = 0, my_end = 0;
     bool sizes_ok = in_range;
       {
@@ -961,7 +1078,7 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
         {
         const uint32_t sz = szs[w];
         if (sz > lz4_block_bound(B) || sz == 0) sizes_ok = false;
-        if (sizes_ok)
+        if (sizes_ok && w == (int)warp)
           {
           const uint8_t* src = a.payload + off;
           const uint32_t al = (uint32_t)reinterpret_cast<uintptr_t>(src) & 15u;
@@ -973,20 +1090,20 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
           const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(planes + (size_t)w * pstride + (d0 - al));
           const uint32_t nv = (al + sz + 15u) >> 4;
           const uint64_t left = a.payload_bytes - off + al;            // bytes from src16 to the end of the payload
-          for (uint32_t i = threadIdx.x; i < nv; i += WB * 32)
+          for (uint32_t i = lane; i < nv; i += 32)
             {
             const uint64_t rem = left - 16ull * i;
             const uint32_t ssz = rem >= 16 ? 16u : (uint32_t)rem;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst_s + 16u * i), "l"(src16 + 16u * i), "r"(ssz) : "memory");
             }
-          if (w == (int)warp) { my_ip = d0; my_end = d0 + sz; }
+          my_ip = d0; my_end = d0 + sz;
           }
         off += sz;
         }
       }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    __syncwarp();
     TB200_PH(2);                                     // staging
 
     // 2. decode in place
