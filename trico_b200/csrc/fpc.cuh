@@ -60,7 +60,12 @@ __host__ __device__ constexpr int fpc_stage_row_words(int sb, int ncomp, int wby
 // its per-value reads see a 4-way bank conflict; 4-byte copies into odd rows cost more than that)
 __host__ __device__ constexpr int fpc_stage_row_words_enc(int sb, int ncomp, int wbytes) { return sb * ncomp * (wbytes / 4) + 4; }
 
-__device__ __forceinline__ int sig_bytes(uint32_t x) { return (39 - __clz((int)x)) >> 3; }
+// significant bytes of x (0 for x = 0): bfind gives the index of the leading one, 0xffffffff for zero
+__device__ __forceinline__ int sig_bytes(uint32_t x)
+  {
+  uint32_t b; asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(x));
+  return (int)((b + 8u) >> 3);
+  }
 __device__ __forceinline__ int sig_bytes(uint64_t x) { return (71 - __clzll((long long)x)) >> 3; }
 
 // byte store to shared memory through its 32-bit window address (one STS, no generic-address
@@ -341,7 +346,7 @@ template <typename W, int SB> struct FpcEncWindow
   {
   using TR = FpcTraits<W>;
   static constexpr int BYTES = 15 + (SB / TR::GROUP) * TR::HDR + SB * TR::WBYTES;
-  static constexpr int VECS = (BYTES + 15) / 16;
+  static constexpr int VECS = ((BYTES + 15) / 16) | 1;     // odd: rows of 44 words spread the lanes' accesses over the banks better than 40
   };
 
 // EXP = (e1 << 8) | e2 compiles the predictor exponents in (the archive default (2,4) runs this
@@ -917,7 +922,8 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
       __syncthreads();                               // the staging tile may be overwritten; window words are visible
       if (i0 + SB < cnt0) stage_in(i0 + SB);         // next slab crosses L2 -> shared memory while the windows drain
 
-      // c. completed vectors of the warp's 32 windows -> the chunks' scratch slots
+      // c. completed vectors of the warp's 32 windows -> the chunks' scratch slots (warp-wide, so the
+      //    stores are whole sectors; every lane flushing its own 16-byte pieces was measured slower)
       const uint32_t nf = wp >> 2;
 #pragma unroll
       for (int it = 0; it < WV; ++it)

@@ -102,6 +102,23 @@ __device__ __forceinline__ uint32_t lz4_emit(DstPtr dst, uint32_t op, const uint
   const unsigned lane = lane_id();
   const uint32_t m = mlen ? mlen - LZ4_MINMATCH : 0;
   const uint32_t next = nlit >= 15 ? (nlit - 15) / 255 + 1 : 0;       // literal-length extension bytes
+    { // a sequence of at most 32 bytes (short literal run, match length continuation included) leaves
+      // as one warp store: lane i produces byte i
+    const uint32_t mext = (mlen && m >= 15) ? (m - 15) / 255 + 1 : 0;
+    const uint32_t total = 1u + next + nlit + (mlen ? 2u + mext : 0u);
+    if (total <= 32u)
+      {
+      const uint32_t l0 = 1u + next, o0 = l0 + nlit;                  // index of the first literal, of the offset's low byte
+      uint32_t byte = ((nlit >= 15 ? 15u : nlit) << 4) | (m >= 15 ? 15u : m);
+      if (lane >= 1u && lane < l0) byte = (lane == next) ? (nlit - 15) % 255 : 255u;
+      if (lane >= l0 && lane < o0) byte = src[lit_start + lane - l0];
+      if (lane == o0) byte = offset & 0xffu;
+      if (lane == o0 + 1u) byte = offset >> 8;
+      if (lane >= o0 + 2u) byte = (lane + 1u == total) ? (m - 15) % 255 : 255u;
+      if (lane < total) dst[op + lane] = (uint8_t)byte;
+      return op + total;
+      }
+    }
   if (lane == 0) dst[op] = (uint8_t)(((nlit >= 15 ? 15u : nlit) << 4) | (m >= 15 ? 15u : m));
   for (uint32_t i = lane; i < next; i += 32) dst[op + 1 + i] = (i + 1 == next) ? (uint8_t)((nlit - 15) % 255) : (uint8_t)255;
   op += 1 + next;
@@ -167,6 +184,44 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
     while (p <= mflimit)
       {
       const uint32_t stride = 1u + (attempts >> 6);
+      uint32_t mq, mc;
+      if (stride >= 2u && (attempts & 32u) == 0)
+        { // Accelerated scan (nothing matched for 64+ positions): two positions per lane and step - the
+          // 64 positions of two consecutive steps with this stride.  The two look-ups are independent,
+          // which is what a lone warp is short of.  (The second half does not see the first half's
+          // inserts; at this distance that costs nothing measurable.)
+        const uint32_t qa = p + lane * stride, qb = qa + 32u * stride;
+        const bool va = qa <= mflimit, vb = qb <= mflimit;
+        const uint32_t sa = va ? smem_read32(src, qa) : 0u, sb = vb ? smem_read32(src, qb) : 0u;
+        const uint32_t ha = (sa * 2654435761u) >> (32 - HLOG), hb = (sb * 2654435761u) >> (32 - HLOG);
+        const uint32_t ca = table[ha], cb = table[hb];
+        const uint32_t ra = smem_read32(src, ca), rb = smem_read32(src, cb);     // table entries are positions inside the block
+        const bool oka = va && ca < qa && ra == sa, okb = vb && cb < qb && rb == sb;
+        const unsigned maska = __ballot_sync(FULL, oka), maskb = __ballot_sync(FULL, okb);
+        const int fa = maska ? __ffs((int)maska) - 1 : 32, fb = maska ? -1 : (maskb ? __ffs((int)maskb) - 1 : 32);
+        // insert the positions up to the chosen match; the highest position of a bucket wins
+        const bool ia = va && (int)lane <= fa, ib = vb && (int)lane <= fb;
+        __syncwarp();
+        if (ia) table[ha] = (uint16_t)qa;
+        __syncwarp();
+        if (ib) table[hb] = (uint16_t)qb;
+        __syncwarp();
+        for (;;)
+          {
+          const bool la = ia && table[ha] < (uint16_t)qa, lb = ib && table[hb] < (uint16_t)qb;
+          if (!__any_sync(FULL, la || lb)) break;
+          if (la) table[ha] = (uint16_t)qa;
+          __syncwarp();
+          if (lb && table[hb] < (uint16_t)qb) table[hb] = (uint16_t)qb;
+          __syncwarp();
+          }
+        if ((maska | maskb) == 0) { p += 64u * stride; attempts += 64; TB200_EPH(0); continue; }
+        const int f = maska ? fa : fb;
+        mq = (maska ? p : p + 32u * stride) + (uint32_t)f * stride;
+        mc = __shfl_sync(FULL, maska ? ca : cb, f);
+        }
+      else
+        {
       const uint32_t q = p + lane * stride;
       const bool valid = q <= mflimit;
       const uint32_t seq = valid ? smem_read32(src, q) : 0u;
@@ -204,10 +259,11 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
         __syncwarp();
         }
       if (mask == 0) { p += 32u * stride; attempts += 32; TB200_EPH(0); continue; }
+      mq = p + (uint32_t)f * stride;
+      mc = __shfl_sync(FULL, cand, f);
+        }
       attempts = 0;
       TB200_EPH(1);
-      uint32_t mq = p + (uint32_t)f * stride;
-      uint32_t mc = __shfl_sync(FULL, cand, f);
       // backward extension over bytes not yet emitted (lz4.c:947-950 does the same serially)
         {
         const uint32_t room = min(min(mq - anchor, mc), 32u);
@@ -233,9 +289,10 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
         else
           {
           len += 128;
+          len -= (mc + len) & 15u;      // back up (over bytes known to be equal) until the candidate side is 16-byte aligned: its vectors are single reads
           while (len < maxlen)
             {
-            const uint4 va = smem_read128u(src, mq + len + 16 * lane), vb = smem_read128u(src, mc + len + 16 * lane);
+            const uint4 va = smem_read128u(src, mq + len + 16 * lane), vb = *reinterpret_cast<const uint4*>(src + mc + len + 16 * lane);
             const uint32_t x0 = va.x ^ vb.x, x1 = va.y ^ vb.y, x2 = va.z ^ vb.z, x3 = va.w ^ vb.w;
             const unsigned nw = __ballot_sync(FULL, (x0 | x1 | x2 | x3) != 0);
             if (nw == 0) { len += 512; continue; }
