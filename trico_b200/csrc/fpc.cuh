@@ -725,6 +725,9 @@ __device__ __forceinline__ void warp_copy_global(uint8_t* __restrict__ dst, cons
   if (done + lane < n) dst[done + lane] = __ldcg(src + done + lane);
   }
 
+#ifndef TB200_FPC_ENC_PREFETCH
+#define TB200_FPC_ENC_PREFETCH 1
+#endif
 #ifndef TB200_FPC_ENC_WARPS
 #define TB200_FPC_ENC_WARPS 15      // resident warps per SM the register allocation aims at
 #endif
@@ -823,6 +826,16 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
           const uint32_t r = ci / (uint32_t)ROWV, v = ci - r * (uint32_t)ROWV;
           asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(stage_s + (r * ROWW + 4u * v) * 4u), "l"(tin + (size_t)r * row_bytes + 16u * v), "l"(pol_first) : "memory");
           }
+#if TB200_FPC_ENC_PREFETCH
+        // the slab after this one -> L2 (one 128-byte line per thread), so that its copy, issued one
+        // sub-block from now, finds the data on the chip instead of waiting for DRAM
+        if (i0 + SB < S)
+          {
+          constexpr uint32_t LPR = ROWV / 8;                           // lines per row segment
+          const uint32_t r = threadIdx.x / LPR, l = threadIdx.x - r * LPR;
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(tin + (size_t)r * row_bytes + (size_t)SB * (NCOMP * sizeof(W)) + 128u * l));
+          }
+#endif
         }
       else
         {
@@ -996,22 +1009,23 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
         sz[0] = (uint8_t)mine; sz[1] = (uint8_t)(mine >> 8);
         }
       }
+    constexpr int BV = 5;                                  // vectors per lane of the bounce path: chunks up to 2560 bytes
+    const bool bounce_path = a.slot <= 32u * BV * 16u && a.slot <= 32u * WV * 16u;
+    uint4 cur[BV], nxt[BV];
+    auto fetch = [&](uint4 (&r)[BV], uint32_t q)
+      {
+      const uint32_t nv = (sh_size[q] + 15u) >> 4;
+      const uint4* s4 = reinterpret_cast<const uint4*>(cta_scr + (size_t)q * a.slot);
+#pragma unroll
+      for (int u = 0; u < BV; ++u) if (lane + 32u * u < nv) r[u] = ld_scratch(s4 + lane + 32 * u);
+      };
+    if (bounce_path) fetch(cur, warp);                     // the first chunk's bytes travel while the look-back finishes
     __syncthreads();
     const uint64_t base = sh_base;
-    constexpr int BV = 5;                                  // vectors per lane of the bounce path: chunks up to 2560 bytes
-    if (a.slot <= 32u * BV * 16u && a.slot <= 32u * WV * 16u)
+    if (bounce_path)
       { // slot -> registers (the next chunk's loads are in flight while this one is written) -> the warp's
         // window area -> final offset; the shared-memory hop turns the alignment shift into cheap LDS work
       uint8_t* bounce = reinterpret_cast<uint8_t*>(win + (size_t)warp * 32 * WV * 4);
-      uint4 cur[BV], nxt[BV];
-      auto fetch = [&](uint4 (&r)[BV], uint32_t q)
-        {
-        const uint32_t nv = (sh_size[q] + 15u) >> 4;
-        const uint4* s4 = reinterpret_cast<const uint4*>(cta_scr + (size_t)q * a.slot);
-#pragma unroll
-        for (int u = 0; u < BV; ++u) if (lane + 32u * u < nv) r[u] = ld_scratch(s4 + lane + 32 * u);
-        };
-      if (warp < (unsigned)NTHREADS) fetch(cur, warp);
       for (uint32_t q = warp; q < (uint32_t)NTHREADS; q += NWARPS)
         {
         if (q + NWARPS < (uint32_t)NTHREADS) fetch(nxt, q + NWARPS);

@@ -519,7 +519,7 @@ __device__ __forceinline__ uint32_t plane_bytes(const uint4 v, uint32_t p)
 #define TB200_LZ4_ENC_LOAD_UN 16     // 16-byte loads in flight per lane while a range is split into planes
 #endif
 template <int WB, int HLOG>
-__global__ void __launch_bounds__(Lz4Cta<WB>::WARPS * 32)
+__global__ void __launch_bounds__(Lz4Cta<WB>::WARPS * 32, Lz4Cta<WB>::WARPS == 4 ? 3 : 2)      // shared memory admits 12 (16) resident warps per SM
 lz4_encode_kernel(const Lz4EncodeArgs a)
   {
   constexpr int WARPS = Lz4Cta<WB>::WARPS;
@@ -530,18 +530,25 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
   uint8_t* buf = smem_raw + (size_t)warp * pstride;
   uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WARPS * pstride) + ((size_t)warp << HLOG);
 
-  // A ticket is a RANGE of B elements; the warp compresses its WB planes one after the other.  The
-  // pass that extracts the first plane also notes in which bits the elements of the range differ at
-  // all: a plane none of whose bits ever changes (the upper planes of index data, mostly) is one
-  // repeated byte and gets its encoding written without being extracted or searched.
-  // Tickets are taken one range ahead so the next range can be pulled towards L2 meanwhile.
+  // A ticket is one HALF of the planes of a range of B elements - the even or the odd ones - which
+  // the warp compresses one after the other.  (The two halves are taken by two warps at about the
+  // same time, so the range crosses from DRAM once; a warp that keeps a range to itself for all
+  // planes holds it for ~60 us, and 1776 such ranges do not fit in L2.)  The pass that extracts the
+  // first plane also notes in which bits the elements of the range differ at all: a plane none of
+  // whose bits ever changes (the upper planes of index data, mostly) is one repeated byte and gets
+  // its encoding written without being extracted or searched.
+  // Tickets are taken one ahead so the next range can be pulled towards L2 meanwhile.
+  constexpr uint32_t HALVES = WB > 1 ? 2 : 1;
+  const uint64_t ntickets = (uint64_t)a.nranges * HALVES;
   uint32_t t32 = 0;
   if (lane == 0) t32 = atomicAdd(a.ticket, 1u);
-  uint64_t k = __shfl_sync(FULL, t32, 0);
-  while (k < a.nranges)
+  uint64_t tk = __shfl_sync(FULL, t32, 0);
+  while (tk < ntickets)
     {
     if (lane == 0) t32 = atomicAdd(a.ticket, 1u);
-    const uint64_t knext = __shfl_sync(FULL, t32, 0);
+    const uint64_t tknext = __shfl_sync(FULL, t32, 0);
+    const uint64_t k = tk / HALVES, knext = tknext / HALVES;
+    const uint32_t half = (uint32_t)(tk % HALVES);
     const uint64_t lo = k << a.log2B;
     const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
     const uint8_t* gin = reinterpret_cast<const uint8_t*>(a.in) + lo * WB;
@@ -549,10 +556,11 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
 
     uint32_t diff_lo = 0xffffffffu, diff_hi = 0xffffffffu;            // bits that differ somewhere in the range (bytes = planes); all set = unknown
     uint32_t e0_lo = 0, e0_hi = 0;                                     // the range's first element
-    for (uint32_t p = 0; p < (uint32_t)WB; ++p)
+#pragma unroll 1
+    for (uint32_t p = half; p < (uint32_t)WB; p += HALVES)
       {
       const uint64_t g = k * WB + p;
-      if (p == (uint32_t)WB - 1u && knext < a.nranges)
+      if (p + HALVES >= (uint32_t)WB && knext != k && knext < a.nranges)
         { // the next range -> L2, a few microseconds before its first pass (earlier and it is evicted again)
         const uint8_t* nx = reinterpret_cast<const uint8_t*>(a.in) + (knext << a.log2B) * WB;
         const uint64_t lim = a.n * WB;
@@ -576,7 +584,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
           const uint32_t nfull = nvec / (32 * UN);                       // whole batches of UN vectors per lane
           const uint32_t sel2 = p | ((2u + p) << 4) | ((4u + p) << 8) | ((6u + p) << 12);
           // first pass over a complete range: collect the differing bits of all planes
-          const bool survey = p == 0 && WB > 1 && cnt == B && nfull * 32 * UN == nvec;
+          const bool survey = p == half && WB > 1 && cnt == B && nfull * 32 * UN == nvec;
           const bool SURVEY = survey;
             {
             uint32_t r_lo = 0, r_hi = 0, d_lo = 0, d_hi = 0;               // reference element (this lane's first), differences to it
@@ -646,7 +654,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
         }
       __syncwarp();
       }
-    k = knext;
+    tk = tknext;
     }
   }
 
@@ -655,7 +663,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
 // no waiting), then the CTA copies the tile's blocks to their final offsets, the bytes spread
 // evenly over its threads.
 constexpr int LZ4_ASM_THREADS = 256;
-constexpr int LZ4_ASM_TILE = 128;
+constexpr int LZ4_ASM_TILE = 128;           // 64 measured the same, 256 slower
 
 __global__ void __launch_bounds__(LZ4_ASM_THREADS)
 lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
