@@ -629,6 +629,7 @@ fpc_decode_kernel(const FpcDecodeArgs a)
       const uint32_t row_bytes = (uint32_t)(NCOMP * sizeof(W)) << a.log2S;
       uint8_t* to = gout + ((((uint64_t)tile * (32 * R)) << a.log2S) + i0) * (NCOMP * sizeof(W)) + (size_t)r0 * row_bytes + 4u * w;
       const uint32_t* from = stagebuf + (size_t)r0 * ROWW + w;
+      const size_t step = (size_t)R * row_bytes;                      // the pointer walks from row to row: one 64-bit add per store
       constexpr int UN = 8;
 #pragma unroll 1
       for (int it0 = 0; it0 < 32; it0 += UN)
@@ -637,7 +638,7 @@ fpc_decode_kernel(const FpcDecodeArgs a)
 #pragma unroll
         for (int u = 0; u < UN; ++u) v[u] = from[(size_t)(it0 + u) * R * ROWW];
 #pragma unroll
-        for (int u = 0; u < UN; ++u) __stcs(reinterpret_cast<uint32_t*>(to + (size_t)(it0 + u) * R * row_bytes), v[u]);
+        for (int u = 0; u < UN; ++u) { __stcs(reinterpret_cast<uint32_t*>(to), v[u]); to += step; }
         }
       }
     else
