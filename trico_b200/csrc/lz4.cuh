@@ -1044,11 +1044,18 @@ __device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip
 
 // ---------------------------------------------------------------------------------------------
 // K6: per-block LZ4 decode fused with the plane merge (trico_transpose_uint*_soa_to_aos,
-// transpose_aos_to_soa.c:94-147).  CTA = WB warps, tile = one range of B elements:
-//   1. the whole CTA stages the tile's WB compressed blocks (contiguous in the payload) into the
-//      tails of the plane buffers with 16-byte cp.async copies, all in flight at once
-//   2. warp p decodes plane p in place (lz4_decode_inplace)
-//   3. the CTA writes the merged elements with 16-byte stores.
+// transpose_aos_to_soa.c:94-147).  CTA = WB warps with one in-place plane buffer each; a tile = one
+// range of B elements = WB blocks, contiguous in the payload.
+//   0. warp 0 runs one step ahead: ticket, block sizes, base offset (look-back), and a look at the
+//      blocks themselves - a block that is exactly the run encoding of lz4_emit_run (one repeated
+//      byte: the upper planes of index data, mostly) needs neither a buffer nor a decoder.  When two
+//      consecutive tiles have at most WB/2 other planes each, the CTA takes them TOGETHER: the tile
+//      time is set by the plane with the most sequences while the other warps wait at the merge
+//      barrier, so two tiles in flight per CTA is twice the throughput.
+//   1. every working warp stages its block into the tail of its buffer (16-byte cp.async copies)
+//      and waits for nothing else
+//   2. it decodes the plane in place (lz4_decode_inplace)
+//   3. the CTA writes the merged elements with 16-byte stores, repeated bytes from registers.
 // ---------------------------------------------------------------------------------------------
 struct Lz4DecodeArgs
   {
@@ -1062,185 +1069,284 @@ struct Lz4DecodeArgs
   uint64_t* desc;
   uint32_t* ticket;
   uint32_t* status;        // set to 1 if any block was malformed
-  unsigned long long* dbg; // phase-cycle counters (experiments; nullptr in production)
   };
 
-#define TB200_PH(i) do { if (a.dbg && lane == 0) { const long long t__ = clock64(); atomicAdd(a.dbg + (i) * 4 + (warp & 3), (unsigned long long)(t__ - t_ph)); t_ph = t__; } } while (0)
+struct Lz4TileInfo
+  {
+  uint64_t base;           // payload offset of the tile's first block
+  uint32_t tile;
+  uint32_t ok;             // sizes plausible and inside the payload
+  uint32_t cmask;          // bit q: plane q is one repeated byte
+  uint32_t cval[2];        // those bytes: byte q & 3 of word q >> 2
+  uint32_t sz[8];
+  };
 
 template <int WB>
-__global__ void __launch_bounds__(WB * 32)
+__global__ void __launch_bounds__(WB * 32, WB == 8 ? 2 : 3)      // what the shared memory of the plane buffers admits
 lz4_decode_kernel(const Lz4DecodeArgs a)
   {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t B = 1u << a.log2B;
   const uint32_t pstride = lz4_inplace_stride(B);
   uint8_t* planes = smem_raw;
-  // the tile being decoded and the one after it: warp 0 fetches the next tile's ticket, sizes and
-  // base offset (look-back) while the slower planes are still decoding, so that chain of global
-  // round trips is off the critical path; it also pulls the next tile's blocks towards L2
-  __shared__ uint32_t sh_tile[2];
-  __shared__ uint64_t sh_base[2];
-  __shared__ uint32_t sh_sz[2][WB];
+  constexpr uint32_t ALLP = (1u << WB) - 1u;
+  constexpr uint32_t HALF = WB / 2;
+  __shared__ Lz4TileInfo sh_info[2][2];            // [step parity][tile of the pair]
+  __shared__ uint32_t sh_ntiles[2];
+  __shared__ Lz4TileInfo sh_carry;                 // a tile that was looked at but could not be paired (warp 0 only)
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  bool has_carry = false;                          // warp 0, uniform
 
-  auto fetch_tile = [&](int slot)
-    { // warp 0 only, all lanes
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(a.ticket, 1u);
-    t = __shfl_sync(FULL, t, 0);
+  // warp 0, all lanes: everything about tile t that does not need a plane buffer
+  auto analyze = [&](uint32_t t, Lz4TileInfo* info)
+    {
     uint32_t mysz = 0;
-    if (t < a.nranges && lane < WB)
+    if (lane < WB)
       {
       const uint8_t* sz = a.sizes + 2 * ((uint64_t)t * WB + lane);
       mysz = (uint32_t)sz[0] | ((uint32_t)sz[1] << 8);
       }
-    uint32_t agg = mysz;
+    uint32_t agg = mysz, pre = mysz;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) agg += __shfl_xor_sync(FULL, agg, o);      // lanes >= WB hold 0
-    uint64_t excl = 0;
-    if (t < a.nranges)
+    for (int o = 1; o < 8; o <<= 1)
       {
-      excl = lookback_exclusive(a.desc, t, agg);
-      // next tile's compressed bytes -> L2
-      const uint8_t* p0 = a.payload + excl;
-      for (uint32_t o = lane * 128u; o < agg; o += 32u * 128u)
-        if (excl + o < a.payload_bytes) asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + o));
+      agg += __shfl_xor_sync(FULL, agg, o);                                   // lanes >= WB hold 0
+      const uint32_t up = __shfl_up_sync(FULL, pre, o);
+      if (lane >= (unsigned)o) pre += up;
       }
-    if (lane < WB) sh_sz[slot][lane] = mysz;
-    if (lane == 0) { sh_tile[slot] = t; sh_base[slot] = excl; }
+    agg = __shfl_sync(FULL, agg, 0);
+    pre -= mysz;                                                               // bytes of the tile's blocks before this lane's
+    const bool sizes_ok = __all_sync(FULL, lane >= WB || (mysz != 0 && mysz <= lz4_block_bound(B)));
+    const uint64_t excl = lookback_exclusive(a.desc, t, agg);
+    const bool ok = sizes_ok && excl + agg <= a.payload_bytes;
+    const uint64_t lo = (uint64_t)t << a.log2B;
+    const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
+    uint32_t cmask = 0, cv0 = 0, cv1 = 0;
+    constexpr int NB = 3;                                    // 32-byte rows of a run block that are looked at: blocks up to 20 KiB
+    const uint32_t m = cnt >= 25u ? cnt - 10u : 15u, mext = (m - 15u) / 255u + 1u, rs = 10u + mext, last = (m - 15u) % 255u;
+    if (ok && cnt >= 25u && rs <= 32u * NB)
+      { // which blocks are the run encoding of lz4_emit_run?  Size first, then every byte; the bytes
+        // of all candidate blocks are requested before any is looked at (one memory round trip)
+      uint32_t bv[WB][NB], v[WB];
+      bool cand[WB];
+#pragma unroll
+      for (int q = 0; q < WB; ++q)
+        {
+        cand[q] = __shfl_sync(FULL, mysz, q) == rs;
+        const uint8_t* blk = a.payload + excl + __shfl_sync(FULL, pre, q);
+        v[q] = 0;
+        if (cand[q]) v[q] = blk[1];
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+          {
+          const uint32_t i = lane + 32u * r;
+          bv[q][r] = 0;
+          if (cand[q] && i < rs) bv[q][r] = blk[i];
+          }
+        }
+#pragma unroll
+      for (int q = 0; q < WB; ++q)
+        {
+        bool same = cand[q];
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+          {
+          const uint32_t i = lane + 32u * r;
+          uint32_t e;
+          if (i == 0) e = 0x1fu; else if (i == 1) e = v[q]; else if (i == 2) e = 1u; else if (i == 3) e = 0u;
+          else if (i < 4u + mext) e = (i + 1u == 4u + mext) ? last : 255u;
+          else if (i == 4u + mext) e = 0x50u; else e = v[q];
+          if (i < rs && bv[q][r] != e) same = false;
+          }
+        if (__all_sync(FULL, same))
+          {
+          cmask |= 1u << q;
+          if (q < 4) cv0 |= v[q] << (8 * q); else cv1 |= v[q] << (8 * (q - 4));
+          }
+        }
+      }
+    if (ok)
+      { // the other blocks -> L2
+      const uint8_t* p0 = a.payload + excl;
+      for (uint32_t o = lane * 128u; o < agg; o += 32u * 128u) asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + o));
+      }
+    if (lane < WB) info->sz[lane] = mysz;
+    if (lane == 0) { info->base = excl; info->tile = t; info->ok = ok; info->cmask = cmask; info->cval[0] = cv0; info->cval[1] = cv1; }
+    __syncwarp();
+    };
+  auto take_ticket = [&]()
+    {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1u);
+    return __shfl_sync(FULL, t, 0);
+    };
+  // warp 0: the tile(s) of the next step
+  auto fetch = [&](int par)
+    {
+    uint32_t n = 0;
+    if (has_carry)
+      {
+      if (lane == 0) sh_info[par][0] = sh_carry;
+      __syncwarp();
+      has_carry = false; n = 1;
+      }
+    else
+      {
+      const uint32_t t = take_ticket();
+      if (t < a.nranges) { analyze(t, &sh_info[par][0]); n = 1; }
+      }
+    if (n == 1 && HALF >= 1 && (uint32_t)__popc(~sh_info[par][0].cmask & ALLP) <= HALF)
+      { // room for a second tile
+      const uint32_t t = take_ticket();
+      if (t < a.nranges)
+        {
+        analyze(t, &sh_carry);
+        if ((uint32_t)__popc(~sh_carry.cmask & ALLP) <= HALF)
+          {
+          if (lane == 0) sh_info[par][1] = sh_carry;
+          n = 2;
+          }
+        else has_carry = true;
+        __syncwarp();
+        }
+      }
+    if (lane == 0) sh_ntiles[par] = n;
+#ifdef TB200_K6_COUNT
+    if (lane == 0 && n) atomicAdd(a.ticket + 1 + n, 1u);
+#endif
     };
 
-  long long t_ph = a.dbg ? clock64() : 0;
-  if (warp == 0) fetch_tile(0);
+  if (warp == 0) fetch(0);
   int cur = 0;
   for (;;)
     {
     __syncthreads();
-    const uint32_t tile = sh_tile[cur];
-    if (tile >= a.nranges) break;
-    TB200_PH(0);                                     // (ticket, sizes and look-back were fetched during the previous tile)
-    const uint64_t lo = (uint64_t)tile << a.log2B;
-    const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
+    const uint32_t ntiles = sh_ntiles[cur];
+    if (ntiles == 0) break;
 
-    uint32_t szs[WB];
-    uint32_t agg = 0;
-#pragma unroll
-    for (int w = 0; w < WB; ++w) { szs[w] = sh_sz[cur][w]; agg += szs[w]; }
-    TB200_PH(1);
-    const uint64_t base = sh_base[cur];
-    const bool in_range = base + agg <= a.payload_bytes;
-
-    // 1. stage: every warp fetches its own block into the tail of its plane buffer, at an offset
-    //    congruent to the global address modulo 16 so that the body moves as 16-byte cp.async copies,
-    //    and waits for nothing else (the plane with the most sequences sets the pace of the tile and
-    //    is usually a few hundred bytes: it starts decoding one memory latency after the ticket)
-    uint32_t my_ip = 0, my_end = 0;
-    bool sizes_ok = in_range;
+    // this warp's plane: alone, tile 0's plane `warp`; in a pair, the first HALF warps take tile 0's
+    // planes that need decoding (in order), the others tile 1's
+    const uint32_t j = (ntiles == 2 && warp >= HALF) ? 1u : 0u;
+    const Lz4TileInfo& ti = sh_info[cur][j];
+    const uint32_t work = ~ti.cmask & ALLP;
+    uint32_t p = warp;
+    bool active = (work >> warp) & 1u;
+    if (ntiles == 2)
       {
-      uint64_t off = base;
-#pragma unroll
-      for (int w = 0; w < WB; ++w)
+      const uint32_t rank = warp - j * HALF;
+      active = rank < (uint32_t)__popc(work);
+      p = active ? __fns(work, 0, (int)rank + 1) : 0u;
+      }
+    const uint64_t lo_t = (uint64_t)ti.tile << a.log2B;
+    const uint32_t cnt_t = (uint32_t)((a.n - lo_t < B) ? (a.n - lo_t) : B);
+    uint32_t my_ip = 0, my_end = 0;
+    if (active && ti.ok)
+      { // 1. stage: the block goes to the tail of the buffer, at an offset congruent to its global
+        //    address modulo 16 so that the body moves as 16-byte cp.async copies; whole vectors from
+        //    the boundary below the block to the boundary above it (the few bytes copied in front of /
+        //    behind the block land on free buffer space; nothing at or past the end of the payload
+        //    is read: src-size operand)
+      uint64_t off = ti.base;
+      for (uint32_t q = 0; q < p; ++q) off += ti.sz[q];
+      const uint32_t sz = ti.sz[p];
+      const uint8_t* src = a.payload + off;
+      const uint32_t al = (uint32_t)reinterpret_cast<uintptr_t>(src) & 15u;
+      const uint32_t d0 = ((pstride - 32u - sz - al) & ~15u) + al;           // block occupies [d0, d0 + sz)
+      const uint8_t* src16 = src - al;
+      const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(planes + (size_t)warp * pstride + (d0 - al));
+      const uint32_t nv = (al + sz + 15u) >> 4;
+      const uint64_t left = a.payload_bytes - off + al;                       // bytes from src16 to the end of the payload
+      for (uint32_t i = lane; i < nv; i += 32)
         {
-        const uint32_t sz = szs[w];
-        if (sz > lz4_block_bound(B) || sz == 0) sizes_ok = false;
-        if (sizes_ok && w == (int)warp)
-          {
-          const uint8_t* src = a.payload + off;
-          const uint32_t al = (uint32_t)reinterpret_cast<uintptr_t>(src) & 15u;
-          const uint32_t d0 = ((pstride - 32u - sz - al) & ~15u) + al;           // block occupies [d0, d0 + sz)
-          // whole 16-byte vectors from the boundary below the block to the boundary above it: the few
-          // bytes copied in front of / behind the block land on free buffer space; nothing at or past
-          // the end of the payload is read (src-size operand)
-          const uint8_t* src16 = src - al;
-          const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(planes + (size_t)w * pstride + (d0 - al));
-          const uint32_t nv = (al + sz + 15u) >> 4;
-          const uint64_t left = a.payload_bytes - off + al;            // bytes from src16 to the end of the payload
-          for (uint32_t i = lane; i < nv; i += 32)
-            {
-            const uint64_t rem = left - 16ull * i;
-            const uint32_t ssz = rem >= 16 ? 16u : (uint32_t)rem;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst_s + 16u * i), "l"(src16 + 16u * i), "r"(ssz) : "memory");
-            }
-          my_ip = d0; my_end = d0 + sz;
-          }
-        off += sz;
+        const uint64_t rem = left - 16ull * i;
+        const uint32_t ssz = rem >= 16 ? 16u : (uint32_t)rem;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst_s + 16u * i), "l"(src16 + 16u * i), "r"(ssz) : "memory");
         }
+      my_ip = d0; my_end = d0 + sz;
       }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    TB200_PH(2);                                     // staging
 
     // 2. decode in place
-    uint32_t got = 0xffffffffu;
-    if (sizes_ok) got = lz4_decode_inplace(planes + (size_t)warp * pstride, my_ip, my_end, cnt);
-    if (got != cnt && lane == 0) *a.status = 1;
-    TB200_PH(3);                                     // decode of this warp's plane
-    if (warp == 0) fetch_tile(cur ^ 1);
-    __syncthreads();
-    TB200_PH(4);                                     // wait for the slowest plane
-
-    // 3. merge: element i = bytes planes[p][i], p = 0..WB-1 (LSB first)
-    uint8_t* gout = reinterpret_cast<uint8_t*>(a.out) + lo * WB;
-    if (WB == 1)
+    if (active)
       {
+      uint32_t got = 0xffffffffu;
+      if (ti.ok) got = lz4_decode_inplace(planes + (size_t)warp * pstride, my_ip, my_end, cnt_t);
+      if (got != cnt_t && lane == 0) *a.status = 1;
+      }
+    else if (!ti.ok && lane == 0) *a.status = 1;
+    if (warp == 0) fetch(cur ^ 1);
+    __syncthreads();
+
+    // 3. merge: element i = bytes plane[q][i], q = 0..WB-1 (LSB first)
+    for (uint32_t jj = 0; jj < ntiles; ++jj)
+      {
+      const Lz4TileInfo& tm = sh_info[cur][jj];
+      const uint32_t cm = tm.cmask, wk = ~cm & ALLP;
+      const uint64_t lo = (uint64_t)tm.tile << a.log2B;
+      const uint32_t cnt = (uint32_t)((a.n - lo < B) ? (a.n - lo) : B);
+      const uint8_t* src[WB];                                  // plane q's buffer (unused when it is a repeated byte)
+      uint32_t cw[WB];                                         // the repeated byte in every byte of a word
+#pragma unroll
+      for (int q = 0; q < WB; ++q)
+        {
+        const uint32_t bi = ntiles == 2 ? jj * HALF + (uint32_t)__popc(wk & ((1u << q) - 1u)) : (uint32_t)q;
+        src[q] = planes + (size_t)(bi < (uint32_t)WB ? bi : 0u) * pstride;
+        cw[q] = ((tm.cval[q >> 2] >> (8 * (q & 3))) & 0xffu) * 0x01010101u;
+        }
+      auto word = [&](int q, uint32_t i) { return (cm >> q) & 1u ? cw[q] : reinterpret_cast<const uint32_t*>(src[q])[i]; };
+      auto half = [&](int q, uint32_t i) { return (cm >> q) & 1u ? (cw[q] & 0xffffu) : (uint32_t)reinterpret_cast<const uint16_t*>(src[q])[i]; };
+      auto byte_of = [&](int q, uint32_t i) { return (cm >> q) & 1u ? (uint8_t)cw[q] : src[q][i]; };
+      uint8_t* gout = reinterpret_cast<uint8_t*>(a.out) + lo * WB;
       if ((reinterpret_cast<uintptr_t>(gout) & 15u) == 0)
         {
-        const uint32_t nvec = cnt >> 4;
-        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) reinterpret_cast<uint4*>(gout)[i] = reinterpret_cast<const uint4*>(planes)[i];
-        for (uint32_t i = (nvec << 4) + threadIdx.x; i < cnt; i += blockDim.x) gout[i] = planes[i];
+        constexpr int EPV = 16 / WB;
+        const uint32_t nvec = cnt / EPV;
+        uint4* g4 = reinterpret_cast<uint4*>(gout);
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x)
+          {
+          uint32_t w[4] = {0, 0, 0, 0};
+          if constexpr (WB == 1)
+            {
+            w[0] = word(0, 4 * i); w[1] = word(0, 4 * i + 1); w[2] = word(0, 4 * i + 2); w[3] = word(0, 4 * i + 3);
+            }
+          else if constexpr (WB == 4)
+            { // 4x4 byte transpose: one word of each plane -> four elements
+            const uint32_t p0 = word(0, i), p1 = word(1, i), p2 = word(2, i), p3 = word(3, i);
+            const uint32_t a01l = __byte_perm(p0, p1, 0x5140), a01h = __byte_perm(p0, p1, 0x7362);   // (p0.b0 p1.b0 p0.b1 p1.b1), (b2.. b3..)
+            const uint32_t a23l = __byte_perm(p2, p3, 0x5140), a23h = __byte_perm(p2, p3, 0x7362);
+            w[0] = __byte_perm(a01l, a23l, 0x5410); w[1] = __byte_perm(a01l, a23l, 0x7632);
+            w[2] = __byte_perm(a01h, a23h, 0x5410); w[3] = __byte_perm(a01h, a23h, 0x7632);
+            }
+          else if constexpr (WB == 2)
+            { // eight elements: one 8-byte group of each plane
+            const uint32_t q0x = word(0, 2 * i), q0y = word(0, 2 * i + 1), q1x = word(1, 2 * i), q1y = word(1, 2 * i + 1);
+            w[0] = __byte_perm(q0x, q1x, 0x5140); w[1] = __byte_perm(q0x, q1x, 0x7362);
+            w[2] = __byte_perm(q0y, q1y, 0x5140); w[3] = __byte_perm(q0y, q1y, 0x7362);
+            }
+          else
+            { // two elements: one 2-byte group of each of the 8 planes
+            uint32_t h[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) h[q] = half(q, i);
+            const uint32_t a01 = __byte_perm(h[0], h[1], 0x5140), a23 = __byte_perm(h[2], h[3], 0x5140);   // e0.b0 e0.b1 e1.b0 e1.b1
+            const uint32_t a45 = __byte_perm(h[4], h[5], 0x5140), a67 = __byte_perm(h[6], h[7], 0x5140);
+            w[0] = __byte_perm(a01, a23, 0x5410); w[1] = __byte_perm(a45, a67, 0x5410);
+            w[2] = __byte_perm(a01, a23, 0x7632); w[3] = __byte_perm(a45, a67, 0x7632);
+            }
+          __stcs(g4 + i, make_uint4(w[0], w[1], w[2], w[3]));
+          }
+        for (uint32_t i = nvec * EPV + threadIdx.x; i < cnt; i += blockDim.x)
+          for (int q = 0; q < WB; ++q) gout[(size_t)i * WB + q] = byte_of(q, i);
         }
       else
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) gout[i] = planes[i];
-      }
-    else if ((reinterpret_cast<uintptr_t>(gout) & 15u) == 0)
-      {
-      constexpr int EPV = 16 / WB;
-      const uint32_t nvec = cnt / EPV;
-      uint4* g4 = reinterpret_cast<uint4*>(gout);
-#pragma unroll 4
-      for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x)
         {
-        uint32_t w[4] = {0, 0, 0, 0};
-        if (WB == 4)
-          { // 4x4 byte transpose: one word of each plane -> four elements
-          const uint32_t p0 = reinterpret_cast<const uint32_t*>(planes)[i];
-          const uint32_t p1 = reinterpret_cast<const uint32_t*>(planes + pstride)[i];
-          const uint32_t p2 = reinterpret_cast<const uint32_t*>(planes + 2 * pstride)[i];
-          const uint32_t p3 = reinterpret_cast<const uint32_t*>(planes + 3 * pstride)[i];
-          const uint32_t a01l = __byte_perm(p0, p1, 0x5140), a01h = __byte_perm(p0, p1, 0x7362);   // (p0.b0 p1.b0 p0.b1 p1.b1), (b2.. b3..)
-          const uint32_t a23l = __byte_perm(p2, p3, 0x5140), a23h = __byte_perm(p2, p3, 0x7362);
-          w[0] = __byte_perm(a01l, a23l, 0x5410); w[1] = __byte_perm(a01l, a23l, 0x7632);
-          w[2] = __byte_perm(a01h, a23h, 0x5410); w[3] = __byte_perm(a01h, a23h, 0x7632);
-          }
-        else if (WB == 2)
-          { // eight elements: one 8-byte group of each plane
-          const uint2 q0 = reinterpret_cast<const uint2*>(planes)[i];
-          const uint2 q1 = reinterpret_cast<const uint2*>(planes + pstride)[i];
-          w[0] = __byte_perm(q0.x, q1.x, 0x5140); w[1] = __byte_perm(q0.x, q1.x, 0x7362);
-          w[2] = __byte_perm(q0.y, q1.y, 0x5140); w[3] = __byte_perm(q0.y, q1.y, 0x7362);
-          }
-        else
-          { // two elements: one 2-byte group of each of the 8 planes
-          uint32_t h[8];
-#pragma unroll
-          for (int p = 0; p < 8; ++p) h[p] = reinterpret_cast<const uint16_t*>(planes + (size_t)p * pstride)[i];
-          const uint32_t a01 = __byte_perm(h[0], h[1], 0x5140), a23 = __byte_perm(h[2], h[3], 0x5140);   // e0.b0 e0.b1 e1.b0 e1.b1
-          const uint32_t a45 = __byte_perm(h[4], h[5], 0x5140), a67 = __byte_perm(h[6], h[7], 0x5140);
-          w[0] = __byte_perm(a01, a23, 0x5410); w[1] = __byte_perm(a45, a67, 0x5410);
-          w[2] = __byte_perm(a01, a23, 0x7632); w[3] = __byte_perm(a45, a67, 0x7632);
-          }
-        __stcs(g4 + i, make_uint4(w[0], w[1], w[2], w[3]));
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+          for (int q = 0; q < WB; ++q) gout[(size_t)i * WB + q] = byte_of(q, i);
         }
-      for (uint32_t i = nvec * EPV + threadIdx.x; i < cnt; i += blockDim.x)
-        for (int p = 0; p < WB; ++p) gout[(size_t)i * WB + p] = planes[p * pstride + i];
       }
-    else
-      {
-      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
-        for (int p = 0; p < WB; ++p) gout[(size_t)i * WB + p] = planes[p * pstride + i];
-      }
-    TB200_PH(5);                                     // merge
     cur ^= 1;
     }
   }
