@@ -158,6 +158,9 @@ __device__ __forceinline__ uint32_t lz4_emit_run(DstPtr dst, uint32_t n, uint32_
   return total;
   }
 
+#ifndef TB200_LZ4_DENSE_SEQ
+#define TB200_LZ4_DENSE_SEQ 24u        // bytes per sequence below which a block counts as dense (0: never)
+#endif
 constexpr uint32_t LZ4_SRC_PAD = 576;    // zeroed bytes the compressor may read past the block end (512-byte match extension steps)
 
 // Compresses src[0..n) (shared memory, LZ4_SRC_PAD zero bytes readable past n) into dst.
@@ -180,7 +183,15 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
     __syncwarp();
     const uint32_t mflimit = n - LZ4_MFLIMIT;        // last position where a match may start
     const uint32_t matchlimit = n - LZ4_LASTLITERALS;
-    uint32_t p = 0, attempts = 0;
+    uint32_t p = 0, attempts = 0, nseq = 0;
+    // Dense mode: data that yields a match every few bytes WITHOUT getting smaller for it (noisy
+    // planes: colours, quantised heights - four equal bytes turn up by chance all the time) pays
+    // for every sequence twice, in this warp's serial parse and in the decoder's.  Once the
+    // sequences of the block average less than TB200_LZ4_DENSE_SEQ bytes and the output so far is
+    // above 90 % of the input, a match has to be 8 bytes long to be taken; failures accelerate the
+    // scan as usual.  (Blocks that do compress with short matches - small meshes' index planes -
+    // never get here.)
+    bool dense = false;
     while (p <= mflimit)
       {
       const uint32_t stride = 1u + (attempts >> 6);
@@ -196,7 +207,12 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
         const uint32_t ha = (sa * 2654435761u) >> (32 - HLOG), hb = (sb * 2654435761u) >> (32 - HLOG);
         const uint32_t ca = table[ha], cb = table[hb];
         const uint32_t ra = smem_read32(src, ca), rb = smem_read32(src, cb);     // table entries are positions inside the block
-        const bool oka = va && ca < qa && ra == sa, okb = vb && cb < qb && rb == sb;
+        bool oka = va && ca < qa && ra == sa, okb = vb && cb < qb && rb == sb;
+        if (dense)
+          {
+          oka = oka && smem_read32(src, ca + 4) == smem_read32(src, qa + 4);
+          okb = okb && smem_read32(src, cb + 4) == smem_read32(src, qb + 4);
+          }
         const unsigned maska = __ballot_sync(FULL, oka), maskb = __ballot_sync(FULL, okb);
         const int fa = maska ? __ffs((int)maska) - 1 : 32, fb = maska ? -1 : (maskb ? __ffs((int)maskb) - 1 : 32);
         // insert the positions up to the chosen match; the highest position of a bucket wins
@@ -241,6 +257,7 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
           if (!ok || near > cand) { cand = near; ok = true; }
           }
         }
+      if (dense) ok = ok && smem_read32(src, cand + 4) == smem_read32(src, q + 4);
       const unsigned mask = __ballot_sync(FULL, ok);
       const int f = mask ? __ffs((int)mask) - 1 : 31;
       // Insert the tested positions up to the chosen match only: later ones are scanned again
@@ -309,6 +326,8 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
       TB200_EPH(2);
       op = lz4_emit(dst, op, src, anchor, mq - anchor, mq - mc, len);
       p = anchor = mq + len;
+      ++nseq;
+      dense = p >= 512u && nseq * TB200_LZ4_DENSE_SEQ > p && 10u * op > 9u * p;
       // like lz4.c:1118, remember one position inside the match tail
       if (lane == 0 && p - 2 <= mflimit) table[(smem_read32(src, p - 2) * 2654435761u) >> (32 - HLOG)] = (uint16_t)(p - 2);
       __syncwarp();
