@@ -480,3 +480,64 @@ def test_c1_bunny_against_reference_archive(ours, oracle, golden):
     ratio_ours = (v.nbytes + t.nbytes) / len(mine)
     print(f"C1 bunny: reference {len(ref_blob)} B (ratio {ratio_ref:.4f}), ours {len(mine)} B (ratio {ratio_ours:.4f}, {100 * (ratio_ours / ratio_ref - 1):+.2f} %)")
     assert ratio_ours >= 0.95 * ratio_ref
+
+
+def _check_lz4_both_ways(dev, oracle, ty, arr, log2c):
+    cnt = arr.size // (3 if ty in (3, 4) else 1)
+    g = dev.encode_stream(ty, arr, cnt, log2c)
+    _, _, back, used = oracle.v1_read_stream(b"Trco\x01\0\0\0" + g, 8)
+    assert used == len(g) and back.tobytes() == arr.tobytes(), (ty, log2c, "gpu-written, oracle-read")
+    assert dev.decode_stream(g).tobytes() == arr.tobytes(), (ty, log2c, "gpu-written")
+    s = oracle.v1_write_stream(ty, arr, cnt, log2c)
+    assert dev.decode_stream(s).tobytes() == arr.tobytes(), (ty, log2c, "oracle-written")
+    return g
+
+
+def test_lz4_constant_planes_and_tile_pairing(dev, oracle):
+    """Planes of one repeated byte are written as run blocks without being searched (encoder survey)
+    and read without a buffer (decoder), and tiles whose other planes fit the CTA's buffers are
+    decoded in pairs.  Every mix: all planes constant, upper planes constant, a plane constant in
+    some tiles only (pairs broken up, a tile carried to the next step), constant inside every lane's
+    share but not across lanes, a ragged last tile, every element width."""
+    rng = np.random.default_rng(21)
+    B = 1 << 10
+    for ty, dt in ((17, np.uint8), (18, np.uint16), (19, np.uint32), (20, np.uint64), (3, np.uint32), (4, np.uint64)):
+        w = np.dtype(dt).itemsize
+        n = 23 * B + 517 if ty not in (3, 4) else 3 * (7 * B + 101)
+        cases = {
+            "all constant": np.full(n, 0x0102030405060708 & (2 ** (8 * w) - 1), np.uint64),
+            "upper planes constant": rng.integers(0, 200, n).astype(np.uint64) | (np.uint64(0xAB) << np.uint64(8 * (w - 1))),
+        }
+        # a plane that is constant in some tiles only: tile t (elements [t*B, (t+1)*B)) has noise in plane 1 when t % 3 == 0
+        tile = np.arange(n) // B
+        v = rng.integers(0, 256, n).astype(np.uint64)
+        if w > 1:
+            v |= np.where(tile % 3 == 0, rng.integers(0, 256, n), 7).astype(np.uint64) << np.uint64(8)
+        cases["plane constant in some tiles"] = v
+        # constant within each lane's share of a tile but different between lanes: 16-byte vector i of a
+        # tile goes to lane i % 32, so make the plane byte depend on the vector index
+        vec = (np.arange(n) * w // 16) % 32
+        cases["constant per lane only"] = (vec.astype(np.uint64) << np.uint64(8 * (w - 1))) | np.uint64(5)
+        for name, arr in cases.items():
+            arr = (arr & np.uint64(2 ** (8 * w) - 1) if w < 8 else arr).astype(dt)
+            g = _check_lz4_both_ways(dev, oracle, ty, arr, 10)
+            if name == "all constant":
+                # one 1 KiB run block is 4 + 4 + 6 = 14 bytes; nothing may be bigger
+                ntile = (arr.size + B - 1) // B
+                sizes = np.frombuffer(g[15:15 + 2 * ntile * w], np.uint16)
+                assert sizes.max() <= 14, (ty, sizes.max())
+
+
+def test_lz4_noisy_and_short_run_planes(dev, oracle):
+    """dense mode (noisy planes: short chance matches are dropped once they do not pay) and streams of
+    very many short sequences stay valid LZ4 and round trip; noise must not expand by more than the
+    block overhead"""
+    rng = np.random.default_rng(22)
+    n = 300000
+    noisy = (128 + 100 * np.sin(np.arange(n) * 0.003) + rng.integers(-4, 5, n)).astype(np.uint8)
+    runs16 = (np.arange(n) >> 4).astype(np.uint8)
+    colour = noisy.astype(np.uint32) | (np.roll(noisy, 7).astype(np.uint32) << 8) | (np.roll(noisy, 13).astype(np.uint32) << 16) | np.uint32(0xFF000000)
+    for ty, arr in ((17, noisy), (17, runs16), (13, colour), (18, noisy[: n // 2 * 2].view(np.uint16))):
+        for log2c in (12, 14):
+            g = _check_lz4_both_ways(dev, oracle, ty, arr, log2c)
+            assert len(g) < arr.nbytes * 1.01 + 64, (ty, log2c, len(g), arr.nbytes)
