@@ -21,6 +21,16 @@
 #define TRICO_MAGIC 0x6f637254u          /* "Trco", trico.c:94 */
 
 static _Thread_local char g_err[256] = "";
+
+/* TRICO_B200_TRACE=1: wall-clock time per phase of the one-shot stream path, printed at exit */
+#include <time.h>
+static double g_tr[8]; static unsigned long g_trn[8]; static int g_trace = -1;
+static const char* const g_trname[8] = {"h2d", "encode launch", "size d2h + sync", "reserve", "stream d2h + sync", "decode upload", "decode launch", "decode d2h + sync"};
+static double tr_now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+static void tr_report(void) { for (int i = 0; i < 8; ++i) if (g_trn[i]) fprintf(stderr, "trico_b200 trace: %-20s %8lu calls %9.1f us each\n", g_trname[i], g_trn[i], 1e6 * g_tr[i] / g_trn[i]); }
+static int tr_on(void) { if (g_trace < 0) { const char* e = getenv("TRICO_B200_TRACE"); g_trace = e && e[0] == '1'; if (g_trace) atexit(tr_report); } return g_trace; }
+#define TR_BEGIN double tr_t0 = tr_on() ? tr_now() : 0
+#define TR_MARK(i) do { if (g_trace) { const double t1 = tr_now(); g_tr[i] += t1 - tr_t0; g_trn[i]++; tr_t0 = t1; } } while (0)
 static void set_err(const char* s) { snprintf(g_err, sizeof(g_err), "%s", s); }
 static void set_dev_err(void) { snprintf(g_err, sizeof(g_err), "%s", tb200_last_error()); }
 const char* trico_b200_last_error(void) { return g_err; }
@@ -101,7 +111,8 @@ static int ensure(uint8_t** buf, uint64_t* cap, uint64_t need, worker* w)
   if (!tb200_ctx_sync(w->ctx)) { set_dev_err(); return 0; }
   if (*buf) tb200_device_free(*buf);
   *buf = NULL; *cap = 0;
-  uint64_t want = need + need / 8 + 4096;
+  uint64_t want = need + need / 2 + 4096;         /* streams of growing size must not reallocate every time */
+  if (want < (16u << 20)) want = 16u << 20;       /* ... and small ones never (cudaFree stalls every thread's stream) */
   uint8_t* p = (uint8_t*)tb200_device_alloc(want);
   if (!p) { set_dev_err(); return 0; }
   *buf = p; *cap = want;
@@ -116,7 +127,7 @@ static int ensure(uint8_t** buf, uint64_t* cap, uint64_t need, worker* w)
  * and plain malloc is used, so an empty archive can still be created and inspected.
  * ------------------------------------------------------------------------------------------ */
 typedef struct { uint8_t* p; uint64_t cap; int pinned; } hostbuf;
-#define POOL_SLOTS 8
+#define POOL_SLOTS 64
 static hostbuf g_pool[POOL_SLOTS];
 static uint64_t g_pool_bytes = 0;
 #define POOL_MAX_BYTES (8ull << 30)
@@ -558,19 +569,25 @@ static int write_stream(void* h, int type, const void* data, uint32_t count)
     if (plan_slabs(&plan, type, count, log2c) && use_pipeline(&plan, raw_bytes))
       return write_stream_pipelined(a, type, (const uint8_t*)data, count, &plan);
     }
+  TR_BEGIN;
   if (raw_bytes && !data_on_device)
     {
     if (!ensure(&w->d_raw, &w->raw_cap, raw_bytes + 64, w)) return 0;
     if (!tb200_memcpy_h2d(w->ctx, w->d_raw, data, raw_bytes)) { set_dev_err(); return 0; }
     d_in = w->d_raw;
     }
+  TR_MARK(0);
   if (!ensure(&w->d_enc, &w->enc_cap, bound, w)) return 0;
   if (!tb200_encode_stream(w->ctx, type, d_in, count, log2c, w->d_enc, w->enc_cap, w->d_scalar)) { set_dev_err(); return 0; }
+  TR_MARK(1);
   uint64_t stream_bytes = 0;
   if (!tb200_memcpy_d2h(w->ctx, &stream_bytes, w->d_scalar, 8) || !tb200_ctx_sync(w->ctx)) { set_dev_err(); return 0; }
+  TR_MARK(2);
   if (stream_bytes < TB200_V1_FIXED_BYTES || stream_bytes > bound) { set_err("encoder returned an impossible size"); return 0; }
   if (!buffer_reserve(a, stream_bytes)) return 0;
+  TR_MARK(3);
   if (!tb200_memcpy_d2h(w->ctx, a->buffer + a->size, w->d_enc, stream_bytes) || !tb200_ctx_sync(w->ctx)) { set_dev_err(); return 0; }
+  TR_MARK(4);
   a->size += stream_bytes;
   if (a->version == 0) { a->version = 1; put32(a->buffer + 4, 1); }
   return 1;

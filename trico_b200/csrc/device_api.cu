@@ -101,7 +101,8 @@ static int ws_prepare(tb200_ctx* c, uint64_t ntiles, uint32_t** ticket, uint64_t
     CK(cudaStreamSynchronize(c->stream));
     if (c->ws) CK(cudaFree(c->ws));
     c->ws = nullptr; c->ws_bytes = 0;
-    const size_t cap = need + need / 2 + 4096;
+    size_t cap = need + need / 2 + 4096;
+    if (cap < (256u << 10)) cap = 256u << 10;            // small streams never come back here (cudaFree stalls every thread's stream)
     CK(cudaMalloc((void**)&c->ws, cap));
     c->ws_bytes = cap;
     }
@@ -118,19 +119,53 @@ static int big_prepare(tb200_ctx* c, size_t need, uint8_t** out)
     CK(cudaStreamSynchronize(c->stream));
     if (c->big) CK(cudaFree(c->big));
     c->big = nullptr; c->big_bytes = 0;
-    CK(cudaMalloc((void**)&c->big, need + 4096));
-    c->big_bytes = need + 4096;
+    size_t cap = need + need / 2 + 4096;             // streams of growing size must not reallocate every time
+    if (cap < (64u << 20)) cap = 64u << 20;
+    CK(cudaMalloc((void**)&c->big, cap));
+    c->big_bytes = cap;
     }
   *out = c->big;
   return 1;
+  }
+
+// Per-launch host work that does not change from call to call - the shared-memory opt-in, the
+// occupancy query - is remembered per (kernel, shared memory size, threads, device): streams of a
+// few hundred kilobytes are launch-overhead bound.
+struct launch_memo { const void* kernel; size_t smem; int threads, device, per_sm, sms; bool optin; };
+static launch_memo* memo_for(const void* kernel, size_t smem, int threads, int device)
+  {
+  static thread_local launch_memo table[32];
+  launch_memo* m = &table[(reinterpret_cast<uintptr_t>(kernel) >> 4) % 32];
+  if (!(m->kernel == kernel && m->smem == smem && m->threads == threads && m->device == device))
+    { m->kernel = kernel; m->smem = smem; m->threads = threads; m->device = device; m->per_sm = -1; m->optin = false; }
+  return m;
   }
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes, const tb200_ctx* c)
   {
   if (bytes > (size_t)c->max_smem_optin) return fail_msg("kernel needs more shared memory than the device offers");
+  launch_memo* m = memo_for(reinterpret_cast<const void*>(kernel), bytes, 0, c->device);
+  if (m->optin) return 1;
   // (static + dynamic) above 48 KiB needs the opt-in; the kernels carry up to ~2 KiB of static shared memory
   if (bytes > 40 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  m->optin = true;
+  return 1;
+  }
+
+// resident CTAs per SM and SM count for a persistent grid
+template <typename K>
+static int persistent_grid(K kernel, int threads, size_t smem, const tb200_ctx* c, int* per_sm, int* sms)
+  {
+  launch_memo* m = memo_for(reinterpret_cast<const void*>(kernel), smem, threads, c->device);
+  if (m->per_sm < 0)
+    {
+    int p = 0, n = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p, kernel, threads, smem));
+    CK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, c->device));
+    m->per_sm = p; m->sms = n;
+    }
+  *per_sm = m->per_sm; *sms = m->sms;
   return 1;
   }
 
@@ -210,8 +245,7 @@ static int launch_fpc_encode_lanes(tb200_ctx* c, FpcEncodeArgs a)
                       (size_t)NWARPS * 32 * ((1u << a.e1) + (1u << a.e2)) * sizeof(W);
   if (!set_smem(fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX>, smem, c)) return 0;
   int per_sm = 0, sms = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX>, NWARPS * 32, smem));
-  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  if (!persistent_grid(fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX>, NWARPS * 32, smem, c, &per_sm, &sms)) return 0;
   if (per_sm < 1) return fail_msg("fpc_encode_lanes_kernel does not fit on an SM");
   // persistent grid, every CTA resident (the look-back relies on it); a CTA reuses its scratch slots
   if (const char* e = getenv("TB200_FPC_ENC_CTAS")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments
