@@ -679,8 +679,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
 
 // Assembly: chunk g's block sits at scratch + g*slot with its size in sizes[g]; tiles of
 // LZ4_ASM_TILE chunks take their base from a look-back over tile totals (all known up front, so
-// no waiting), then the CTA copies the tile's blocks to their final offsets, the bytes spread
-// evenly over its threads.
+// no waiting), then the CTA copies the tile's blocks to their final offsets.
 constexpr int LZ4_ASM_THREADS = 256;
 constexpr int LZ4_ASM_TILE = 128;           // 64 measured the same, 256 slower
 
@@ -727,82 +726,67 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
       }
     }
   __syncthreads();
-  // The tile's output is one contiguous byte range; its 16-byte destination vectors are dealt to the
-  // threads round robin, whatever chunk they belong to (blocks of an incompressible plane are 200
-  // times larger than those of a constant one: a chunk-per-warp split leaves most warps idle).
-  // A vector that lies inside one chunk is built from the two aligned source vectors around it;
-  // vectors on a chunk boundary or at the ragged ends of the tile are copied byte by byte.
+  // Large blocks (an incompressible plane is 200 times larger than a constant one) are copied by the
+  // whole CTA, one after the other: 16-byte stores to the aligned body of the destination, each
+  // built from the two aligned source vectors around it (the shift is the same for the whole
+  // block).  Small blocks take one warp each, byte by byte.
   const uint32_t nloc = (uint32_t)((nchunks - g0 < (uint64_t)LZ4_ASM_TILE) ? (nchunks - g0) : (uint64_t)LZ4_ASM_TILE);
   uint8_t* D = a.payload + sh_base;
-  const uint32_t lead = (uint32_t)reinterpret_cast<uintptr_t>(D) & 15u;          // tile byte t lives in vector (t + lead) / 16
-  uint8_t* D16 = D - lead;
-  const uint32_t nvec = (tsum + lead + 15u) >> 4;
   const uint8_t* sbase = a.scratch + g0 * a.slot;
-  uint32_t c = 0;                                                                  // chunk of the previous vector: positions only grow
-  constexpr int UN = 4;
-  for (uint32_t j0 = threadIdx.x; j0 < nvec; j0 += LZ4_ASM_THREADS * UN)
+  constexpr uint32_t BIG = 512;
+  for (uint32_t c = 0; c < nloc; ++c)
     {
-    uint4 va[UN], vb[UN];
-    uint32_t mis[UN], kind[UN], cu[UN];                                            // kind: 0 nothing, 1 vector path, 2 byte path
-#pragma unroll
-    for (int u = 0; u < UN; ++u)
+    const uint32_t nbytes = sh_sz[c];
+    if (nbytes < BIG) continue;
+    const uint8_t* src = sbase + (size_t)c * a.slot;                           // 16-byte aligned, one spare vector behind every block
+    uint8_t* dst = D + sh_off[c];
+    const uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+    if (threadIdx.x < head) dst[threadIdx.x] = __ldcs(src + threadIdx.x);
+    const uint32_t nvec = (nbytes - head) >> 4;
+    uint4* dv = reinterpret_cast<uint4*>(dst + head);
+    const uint4* sv = reinterpret_cast<const uint4*>(src);                      // vector i of the body = source bytes [head + 16 i, head + 16 i + 16)
+    const unsigned sh = (head & 3u) * 8u;
+    const uint32_t ws = head >> 2;                                              // 0..3, the same for the whole block
+    constexpr int UN = 4;
+    for (uint32_t i0 = threadIdx.x; i0 < nvec; i0 += LZ4_ASM_THREADS * UN)
       {
-      const uint32_t j = j0 + (uint32_t)u * LZ4_ASM_THREADS;
-      kind[u] = 0; mis[u] = 0; cu[u] = 0;
-      if (j >= nvec) continue;
-      const int32_t t0 = (int32_t)(16u * j) - (int32_t)lead;                      // tile byte of the vector's first byte
-      const uint32_t tf = t0 < 0 ? 0u : (uint32_t)t0;
-      while (c + 1 < nloc && tf >= sh_off[c] + sh_sz[c]) ++c;
-      cu[u] = c;
-      const uint32_t lo = sh_off[c];
-      if (t0 >= (int32_t)lo && (uint32_t)t0 + 16u <= lo + sh_sz[c])
+      uint4 va[UN], vb[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
         {
-        const uint8_t* src = sbase + (size_t)c * a.slot + ((uint32_t)t0 - lo);     // slots are 16-byte aligned, one spare vector behind every block
-        mis[u] = (uint32_t)reinterpret_cast<uintptr_t>(src) & 15u;
-        const uint4* s16 = reinterpret_cast<const uint4*>(src - mis[u]);
-        va[u] = __ldcs(s16); vb[u] = __ldcs(s16 + 1);
-        kind[u] = 1;
+        const uint32_t i = i0 + (uint32_t)u * LZ4_ASM_THREADS;
+        if (i < nvec) { va[u] = __ldcs(sv + i); if (head) vb[u] = __ldcs(sv + i + 1); }
         }
-      else kind[u] = 2;
-      }
 #pragma unroll
-    for (int u = 0; u < UN; ++u)
-      {
-      const uint32_t j = j0 + (uint32_t)u * LZ4_ASM_THREADS;
-      if (kind[u] == 1)
+      for (int u = 0; u < UN; ++u)
         {
-        const uint32_t w[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-        const unsigned sh = (mis[u] & 3u) * 8u;
-        uint4 o;
-        switch (mis[u] >> 2)
+        const uint32_t i = i0 + (uint32_t)u * LZ4_ASM_THREADS;
+        if (i >= nvec) continue;
+        uint4 o = va[u];
+        if (head)
           {
-          case 0: o = make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh)); break;
-          case 1: o = make_uint4(__funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh)); break;
-          case 2: o = make_uint4(__funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh)); break;
-          default: o = make_uint4(__funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh), __funnelshift_r(w[6], w[7], sh)); break;
+          const uint32_t w[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+          switch (ws)
+            {
+            case 0: o = make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh)); break;
+            case 1: o = make_uint4(__funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh)); break;
+            case 2: o = make_uint4(__funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh)); break;
+            default: o = make_uint4(__funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh), __funnelshift_r(w[6], w[7], sh)); break;
+            }
           }
-        *reinterpret_cast<uint4*>(D16 + 16u * (size_t)j) = o;
-        }
-      else if (kind[u] == 2)
-        { // all sixteen source bytes are requested before any is stored (one memory latency, not sixteen)
-        uint32_t cc = cu[u];
-        uint32_t val[16];
-        unsigned okm = 0;
-#pragma unroll
-        for (uint32_t b = 0; b < 16u; ++b)
-          {
-          const int32_t t = (int32_t)(16u * j + b) - (int32_t)lead;
-          val[b] = 0;
-          if (t < 0 || (uint32_t)t >= tsum) continue;
-          while (cc + 1 < nloc && (uint32_t)t >= sh_off[cc] + sh_sz[cc]) ++cc;
-          val[b] = __ldcs(sbase + (size_t)cc * a.slot + ((uint32_t)t - sh_off[cc]));
-          okm |= 1u << b;
-          }
-#pragma unroll
-        for (uint32_t b = 0; b < 16u; ++b)
-          if (okm & (1u << b)) D16[16u * (size_t)j + b] = (uint8_t)val[b];
+        dv[i] = o;
         }
       }
+    const uint32_t done = head + (nvec << 4);
+    if (done + threadIdx.x < nbytes) dst[done + threadIdx.x] = __ldcs(src + done + threadIdx.x);
+    }
+  for (uint32_t c = warp; c < nloc; c += LZ4_ASM_THREADS / 32)
+    {
+    const uint32_t nbytes = sh_sz[c];
+    if (nbytes >= BIG) continue;
+    const uint8_t* src = sbase + (size_t)c * a.slot;
+    uint8_t* dst = D + sh_off[c];
+    for (uint32_t i = lane; i < nbytes; i += 32) dst[i] = __ldcs(src + i);
     }
   }
 
