@@ -49,7 +49,7 @@ for name, ty, data, cnt in cases:
     hdr = dev.download(d_out.ptr, 16).tobytes()
     def dec(): dev.decode_stream_device(hdr, d_out.ptr, nbytes, d_back.ptr)
     dec(); dev.sync()
-    assert dev.download(d_back.ptr, data.nbytes).tobytes() == data.tobytes(), name
+    if not os.environ.get("NOVERIFY"): assert dev.download(d_back.ptr, data.nbytes).tobytes() == data.tobytes(), name
     res = []
     for f in (enc, dec):
         f(); dev.sync()

@@ -37,17 +37,19 @@ __device__ __forceinline__ void lb_store(uint64_t* p, uint64_t v)
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
   }
 
-// Called by ONE full warp of the tile. Publishes `aggregate` for `tile` and returns the exclusive
-// prefix (sum of all earlier tiles' aggregates) to every lane.
-__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint32_t tile, uint64_t aggregate)
+// Called by ONE full warp of the tile: publishes `aggregate` for `tile` (tile 0: as the inclusive
+// prefix it is).
+__device__ __forceinline__ void lookback_publish(uint64_t* desc, uint32_t tile, uint64_t aggregate)
+  {
+  if (lane_id() == 0) lb_store(desc + tile, (tile == 0 ? LB_INC : LB_AGG) | aggregate);
+  }
+
+// Called by ONE full warp of the tile, after lookback_publish: returns the exclusive prefix (sum
+// of all earlier tiles' aggregates) to every lane and publishes the tile's inclusive prefix.
+__device__ __forceinline__ uint64_t lookback_walk(uint64_t* desc, uint32_t tile, uint64_t aggregate)
   {
   const unsigned lane = lane_id();
-  if (tile == 0)
-    {
-    if (lane == 0) lb_store(desc, LB_INC | aggregate);
-    return 0;
-    }
-  if (lane == 0) lb_store(desc + tile, LB_AGG | aggregate);
+  if (tile == 0) return 0;
   uint64_t excl = 0;
   int64_t look = (int64_t)tile - 1;           // lane 0 inspects `look`, lane i inspects look - i
   for (;;)
@@ -71,6 +73,13 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint32_t 
     }
   if (lane == 0) lb_store(desc + tile, LB_INC | (excl + aggregate));
   return excl;
+  }
+
+// Publishes `aggregate` for `tile` and returns the exclusive prefix to every lane.
+__device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* desc, uint32_t tile, uint64_t aggregate)
+  {
+  lookback_publish(desc, tile, aggregate);
+  return lookback_walk(desc, tile, aggregate);
   }
 
 // ---------------------------------------------------------------------------------------------

@@ -228,34 +228,46 @@ extern "C" uint64_t tb200_v1_stream_bound(int type, uint32_t count, int log2_chu
 // ------------------------------------------------------------------------------------------------
 // chunked FPC
 // ------------------------------------------------------------------------------------------------
-template <typename W, int NCOMP, int R, int SB, int EXP = -1>
+template <typename W, int NCOMP, int R, int SB, int EXP = -1, int DEFER = -1>
 static int launch_fpc_encode_lanes(tb200_ctx* c, FpcEncodeArgs a)
   {
-  if (EXP < 0)   // the archive default exponents run a build with the shifts and masks compiled in
-    return (a.e1 == 2 && a.e2 == 4) ? launch_fpc_encode_lanes<W, NCOMP, R, SB, 0x0204>(c, a) : launch_fpc_encode_lanes<W, NCOMP, R, SB, 0>(c, a);
-  constexpr int EX = EXP < 0 ? 0 : EXP;
   using WIN = FpcEncWindow<W, SB>;
   constexpr int NWARPS = NCOMP * R;
   const uint32_t S = 1u << a.log2S;
+  const uint32_t slot = (fpc_chunk_bound(S, sizeof(W)) + 16u + 15u) & ~15u;
+  if (EXP < 0)   // the archive default exponents run a build with the shifts and masks compiled in
+    return (a.e1 == 2 && a.e2 == 4) ? launch_fpc_encode_lanes<W, NCOMP, R, SB, 0x0204>(c, a) : launch_fpc_encode_lanes<W, NCOMP, R, SB, 0>(c, a);
+  constexpr int EX = EXP < 0 ? 0 : EXP;
+  if (DEFER < 0)
+    { // float vec3 streams of default geometry drain every tile during the next one (a bounce buffer per
+      // warp in shared memory, two sets of scratch slots); the other shapes would lose a resident CTA to it
+    constexpr bool CAN = sizeof(W) == 4 && NCOMP == 3 && R == 1;
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("TB200_FPC_ENC_NODEFER"); off = e && e[0] == '1'; }
+    if (CAN && !off && slot <= 2560u) return launch_fpc_encode_lanes<W, NCOMP, R, SB, EX, CAN ? 1 : 0>(c, a);
+    return launch_fpc_encode_lanes<W, NCOMP, R, SB, EX, 0>(c, a);
+    }
+  constexpr bool DF = DEFER > 0;
   a.ntiles = (a.nranges + 32 * R - 1) / (32 * R);
   if (!ws_prepare(c, a.ntiles + 1, &a.ticket, &a.desc)) return 0;
   if (!a.total_field) a.total_field = reinterpret_cast<uint8_t*>(a.desc + a.ntiles);
   const size_t smem = (size_t)NWARPS * 32 * WIN::VECS * 16 +
                       (size_t)32 * R * fpc_stage_row_words_enc(SB, NCOMP, sizeof(W)) * 4 +
-                      (size_t)NWARPS * 32 * ((1u << a.e1) + (1u << a.e2)) * sizeof(W);
-  if (!set_smem(fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX>, smem, c)) return 0;
+                      (size_t)NWARPS * 32 * ((1u << a.e1) + (1u << a.e2)) * sizeof(W) +
+                      (DF ? (size_t)NWARPS * slot : 0);
+  if (!set_smem(fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX, DF>, smem, c)) return 0;
   int per_sm = 0, sms = 0;
-  if (!persistent_grid(fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX>, NWARPS * 32, smem, c, &per_sm, &sms)) return 0;
+  if (!persistent_grid(fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX, DF>, NWARPS * 32, smem, c, &per_sm, &sms)) return 0;
   if (per_sm < 1) return fail_msg("fpc_encode_lanes_kernel does not fit on an SM");
   // persistent grid, every CTA resident (the look-back relies on it); a CTA reuses its scratch slots
   if (const char* e = getenv("TB200_FPC_ENC_CTAS")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments
   uint32_t grid = (uint32_t)per_sm * (uint32_t)sms;
   if (grid > a.ntiles) grid = a.ntiles;
-  a.slot = (fpc_chunk_bound(S, sizeof(W)) + 16u + 15u) & ~15u;
+  a.slot = slot;
   uint8_t* scratch = nullptr;
-  if (!big_prepare(c, (size_t)grid * NWARPS * 32 * a.slot + 64, &scratch)) return 0;
+  if (!big_prepare(c, (size_t)grid * (DF ? 2 : 1) * NWARPS * 32 * a.slot + 64, &scratch)) return 0;
   a.scratch = scratch;
-  fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX><<<grid, NWARPS * 32, smem, c->stream>>>(a);
+  fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX, DF><<<grid, NWARPS * 32, smem, c->stream>>>(a);
   c->launches++;
   CK(cudaGetLastError());
   return 1;

@@ -346,7 +346,7 @@ template <typename W, int SB> struct FpcEncWindow
   {
   using TR = FpcTraits<W>;
   static constexpr int BYTES = 15 + (SB / TR::GROUP) * TR::HDR + SB * TR::WBYTES;
-  static constexpr int VECS = ((BYTES + 15) / 16) | 1;     // odd: rows of 44 words spread the lanes' accesses over the banks better than 40
+  static constexpr int VECS = (BYTES + 15) / 16;
   };
 
 // EXP = (e1 << 8) | e2 compiles the predictor exponents in (the archive default (2,4) runs this
@@ -732,7 +732,12 @@ __device__ __forceinline__ void warp_copy_global(uint8_t* __restrict__ dst, cons
 #ifndef TB200_FPC_ENC_WARPS
 #define TB200_FPC_ENC_WARPS 15      // resident warps per SM the register allocation aims at
 #endif
-template <typename W, int NCOMP, int R, int SB, int EXP>
+// DEFER: the tile's chunks are not copied out at its end but in small pieces during the NEXT tile,
+// two chunks per warp and sub-block through a per-warp bounce buffer filled by cp.async while the
+// lanes encode (needs two sets of scratch slots per CTA).  Neither the look-back of the tile - its
+// predecessors finish at about the same time, so it used to wait for the slowest of the wave - nor
+// the read-back of the slots is waited for any more.
+template <typename W, int NCOMP, int R, int SB, int EXP, bool DEFER>
 #ifdef TB200_FPC_ENC_MAXNREG
 __global__ void __maxnreg__(TB200_FPC_ENC_MAXNREG)
 #else
@@ -761,6 +766,11 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
   __shared__ uint32_t sh_off[NTHREADS];
   __shared__ uint32_t sh_wsum[NWARPS];
   __shared__ uint64_t sh_base;
+  // DEFER: sizes, offsets, total and base of the tile that is being drained
+  __shared__ uint32_t sh_size_p[DEFER ? NTHREADS : 1];
+  __shared__ uint32_t sh_off_p[DEFER ? NTHREADS : 1];
+  __shared__ uint32_t sh_tsum_p;
+  __shared__ uint64_t sh_base_p;
 
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t c = warp % NCOMP, rgrp = warp / NCOMP;
@@ -773,8 +783,15 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
   const uint4* wwarp4 = reinterpret_cast<const uint4*>(win + (size_t)warp * 32 * WV * 4);
   const uint32_t* srow = stagebuf + (size_t)klocal * ROWW + c * WPV;
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stagebuf);
-  uint8_t* cta_scr = a.scratch + (size_t)blockIdx.x * NTHREADS * a.slot;
+  const size_t set_bytes = (size_t)NTHREADS * a.slot;                                  // one set of scratch slots
+  uint8_t* const scr0 = a.scratch + (size_t)blockIdx.x * (DEFER ? 2 : 1) * set_bytes;
+  uint8_t* cta_scr = scr0;
   uint8_t* my_scr = cta_scr + (size_t)(klocal * NCOMP + c) * a.slot;
+  // DEFER state (uniform over the CTA unless noted)
+  uint8_t* bounce_d = reinterpret_cast<uint8_t*>(tables + (size_t)NWARPS * (nt1 + nt2) * 32) + (size_t)warp * a.slot;   // per warp
+  const uint32_t bounce_s = (uint32_t)__cvta_generic_to_shared(bounce_d);
+  bool pv_valid = false, pv_have_base = false, pv_loaded = false;                       // pv_loaded: per warp
+  uint32_t pv_tile = 0, pv_set = 0, cur_set = 0, pv_next = 0, pv_cur = 0;              // pv_next, pv_cur: per warp
   const uint8_t* gin = reinterpret_cast<const uint8_t*>(a.in);
   const bool in_aligned = (reinterpret_cast<uintptr_t>(gin) & 15u) == 0;
   // L2 residency: the input is read once (evict first); the scratch slots are written now and read
@@ -789,6 +806,58 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
     uint4 w;
     asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p), "l"(pol_first) : "memory");
     return w;
+    };
+  // DEFER: the bounce buffer's chunk -> its final place in the payload
+  auto pv_write = [&]()
+    {
+    const uint32_t nbytes = sh_size_p[pv_cur];
+    if (nbytes) warp_copy_smem_to_global(a.payload + sh_base_p + sh_off_p[pv_cur], bounce_d, nbytes);
+    __syncwarp();
+    pv_loaded = false;
+    };
+  // DEFER: the warp's next chunk of the previous tile, scratch slot -> bounce buffer (asynchronously)
+  auto pv_fetch = [&]()
+    {
+    if (pv_next >= (uint32_t)NTHREADS) return;
+    const uint32_t q = pv_next;
+    const uint32_t nv = (sh_size_p[q] + 15u) >> 4;
+    const uint8_t* sp = scr0 + pv_set * set_bytes + (size_t)q * a.slot;
+    for (uint32_t i = lane; i < nv; i += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(bounce_s + 16u * i), "l"(sp + 16u * i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pv_cur = q; pv_next += NWARPS; pv_loaded = true;
+    };
+  // DEFER: base offset of the previous tile (warp 0; the others see it after the next barrier)
+  auto pv_lookback = [&]()
+    {
+    if (warp != 0) return;
+    const uint64_t excl = lookback_walk(a.desc, pv_tile, sh_tsum_p);
+    if (lane == 0)
+      {
+      sh_base_p = excl;
+      if (pv_tile == a.ntiles - 1)
+        {
+        *a.total = excl + sh_tsum_p;
+        store_u64_bytes(a.total_field, excl + sh_tsum_p);
+        }
+      }
+    };
+  // DEFER: whatever is left of the previous tile, waiting for every copy (end of a tile / of the kernel)
+  auto pv_finish = [&]()
+    {
+    if (!pv_valid) return;
+    if (!pv_have_base) { pv_lookback(); __syncthreads(); pv_have_base = true; }
+    while (pv_loaded || pv_next < (uint32_t)NTHREADS)
+      {
+      if (pv_loaded)
+        {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        pv_write();
+        }
+      pv_fetch();
+      }
+    pv_valid = false;
     };
 
   for (;;)
@@ -809,6 +878,11 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
     const uint64_t lo0 = ((uint64_t)tile * (32 * R)) << a.log2S;
     const uint32_t cnt0 = (uint32_t)((a.n - lo0 < S) ? (a.n - lo0) : S);
     const bool fast_in = ((uint64_t)tile + 1) * (32 * R) < a.nranges && in_aligned;   // every range of the tile is complete
+    if (DEFER)
+      {
+      cta_scr = scr0 + cur_set * set_bytes;
+      my_scr = cta_scr + (size_t)(klocal * NCOMP + c) * a.slot;
+      }
 
     for (uint32_t i = 0; i < nt1 + nt2; ++i) T1[(size_t)i * 32] = 0;
     W pred1 = 0, pred2 = 0, last = 0;
@@ -860,6 +934,11 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
       {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
+      if (DEFER && pv_valid)
+        { // a piece of the previous tile: the chunk that arrived in the bounce buffer leaves, the next one is requested
+        if (!pv_have_base && i0 >= (uint32_t)SB) pv_lookback();      // one sub-block after the tile's end its predecessors have published
+        if (pv_have_base) { if (pv_loaded) pv_write(); pv_fetch(); }
+        }
 
       // b. encode up to SB values of this lane's chunk
       const uint32_t todo = (i0 < cnt) ? ((cnt - i0 < (uint32_t)SB) ? cnt - i0 : (uint32_t)SB) : 0;
@@ -934,6 +1013,20 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
           }
         }
       __syncthreads();                               // the staging tile may be overwritten; window words are visible
+      if (DEFER && pv_valid)
+        {
+        if (!pv_have_base && i0 >= (uint32_t)SB) pv_have_base = true;       // warp 0 stored the base before the barrier
+        if (pv_have_base)
+          {
+          if (pv_loaded)
+            {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");          // requested a whole encode ago
+            __syncwarp();
+            pv_write();
+            }
+          pv_fetch();
+          }
+        }
       if (i0 + SB < cnt0) stage_in(i0 + SB);         // next slab crosses L2 -> shared memory while the windows drain
 
       // c. completed vectors of the warp's 32 windows -> the chunks' scratch slots (warp-wide, so the
@@ -989,6 +1082,25 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
 #pragma unroll
       for (int w = 0; w < NWARPS; ++w) { const uint32_t t = sh_wsum[w]; if (w < (int)warp) wbase += t; tsum += t; }
       sh_off[threadIdx.x] = wbase + incl - mine;
+      if (DEFER)
+        { // u16 size table, stream order
+        const uint64_t gq = (uint64_t)tile * NTHREADS + threadIdx.x;
+        if (gq < (uint64_t)a.nranges * NCOMP)
+          {
+          uint8_t* sz = a.sizes + 2 * gq;
+          sz[0] = (uint8_t)mine; sz[1] = (uint8_t)(mine >> 8);
+          }
+        if (warp == 0) lookback_publish(a.desc, tile, tsum);      // later tiles can add this one up; its own base is looked up during the next tile
+        pv_finish();                                              // what is left of the tile before this one
+        __syncthreads();                                          // nobody reads the previous tile's tables or bounce buffers any more
+        sh_size_p[threadIdx.x] = mine;
+        sh_off_p[threadIdx.x] = wbase + incl - mine;
+        if (threadIdx.x == 0) sh_tsum_p = tsum;
+        pv_valid = true; pv_have_base = false; pv_loaded = false;
+        pv_tile = tile; pv_set = cur_set; pv_next = warp;
+        cur_set ^= 1u;
+        continue;
+        }
       if (warp == 0)
         {
         const uint64_t excl = lookback_exclusive(a.desc, tile, tsum);
@@ -1020,6 +1132,9 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
 #pragma unroll
       for (int u = 0; u < BV; ++u) if (lane + 32u * u < nv) r[u] = ld_scratch(s4 + lane + 32 * u);
       };
+#ifdef TB200_FPC_ENC_NODRAIN
+    continue;                                              // experiment: upper bound of what hiding the tile epilogue could gain (output is garbage)
+#endif
     if (bounce_path) fetch(cur, warp);                     // the first chunk's bytes travel while the look-back finishes
     __syncthreads();
     const uint64_t base = sh_base;
@@ -1048,6 +1163,7 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
         if (nbytes) warp_copy_global(a.payload + base + sh_off[q], cta_scr + (size_t)q * a.slot, nbytes);
         }
     }
+  if (DEFER) pv_finish();
   }
 
 // ---------------------------------------------------------------------------------------------
