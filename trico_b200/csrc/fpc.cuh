@@ -1132,9 +1132,6 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
 #pragma unroll
       for (int u = 0; u < BV; ++u) if (lane + 32u * u < nv) r[u] = ld_scratch(s4 + lane + 32 * u);
       };
-#ifdef TB200_FPC_ENC_NODRAIN
-    continue;                                              // experiment: upper bound of what hiding the tile epilogue could gain (output is garbage)
-#endif
     if (bounce_path) fetch(cur, warp);                     // the first chunk's bytes travel while the look-back finishes
     __syncthreads();
     const uint64_t base = sh_base;
