@@ -158,6 +158,9 @@ __device__ __forceinline__ uint32_t lz4_emit_run(DstPtr dst, uint32_t n, uint32_
   return total;
   }
 
+#ifndef TB200_LZ4_DENSE_MIN
+#define TB200_LZ4_DENSE_MIN 512u       // bytes of a block that are parsed before the decision
+#endif
 #ifndef TB200_LZ4_DENSE_SEQ
 #define TB200_LZ4_DENSE_SEQ 24u        // bytes per sequence below which a block counts as dense (0: never)
 #endif
@@ -327,7 +330,7 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
       op = lz4_emit(dst, op, src, anchor, mq - anchor, mq - mc, len);
       p = anchor = mq + len;
       ++nseq;
-      dense = p >= 512u && nseq * TB200_LZ4_DENSE_SEQ > p && 10u * op > 9u * p;
+      dense = p >= TB200_LZ4_DENSE_MIN && nseq * TB200_LZ4_DENSE_SEQ > p && 10u * op > 9u * p;
       // like lz4.c:1118, remember one position inside the match tail
       if (lane == 0 && p - 2 <= mflimit) table[(smem_read32(src, p - 2) * 2654435761u) >> (32 - HLOG)] = (uint16_t)(p - 2);
       __syncwarp();
