@@ -195,11 +195,16 @@ extern "C" int tb200_default_log2_chunk(int type, uint32_t count)
   if (codec == 1) return w == 4 ? 9 : 8;     // 512 floats / 256 doubles per chunk (ratio cost <= 1 %)
   if (codec == 2)
     {
-    // 16 KiB plane blocks (8 KiB for 8-byte elements: 8 planes share one CTA); TB200_LZ4_LOG2B overrides (experiments)
+    // 16 KiB plane blocks for index streams and the 1- and 4-byte attribute lists; 8 KiB for 8-byte
+    // elements (8 planes share one CTA) and for colours and 2-byte lists: those are mostly noise or
+    // very many short sequences, which a warp parses serially - twice the blocks in flight is
+    // +30..75 % there for 0.0..0.4 % of ratio (u8 lists with long-range repeats lose 40 %: they stay
+    // at 16 KiB).  TB200_LZ4_LOG2B overrides (experiments).
     static int env = -1;
     if (env < 0) { const char* e = getenv("TB200_LZ4_LOG2B"); env = e ? atoi(e) : 0; }
     if (env >= 8 && env <= 15) return w == 8 ? (env > 14 ? 14 : env) : env;
-    return w == 8 ? 13 : 14;
+    if (w == 8 || w == 2 || type == 13 || type == 14) return 13;
+    return 14;
     }
   return 0;
   }
