@@ -1217,9 +1217,6 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
         }
       }
     if (lane == 0) sh_ntiles[par] = n;
-#ifdef TB200_K6_COUNT
-    if (lane == 0 && n) atomicAdd(a.ticket + 1 + n, 1u);
-#endif
     };
 
   if (warp == 0) fetch(0);
