@@ -134,8 +134,8 @@ static int big_prepare(tb200_ctx* c, size_t need, uint8_t** out)
 struct launch_memo { const void* kernel; size_t smem; int threads, device, per_sm, sms; bool optin; };
 static launch_memo* memo_for(const void* kernel, size_t smem, int threads, int device)
   {
-  static thread_local launch_memo table[32];
-  launch_memo* m = &table[(reinterpret_cast<uintptr_t>(kernel) >> 4) % 32];
+  static thread_local launch_memo table[2][32];            // [0] shared-memory opt-in (threads == 0), [1] occupancy
+  launch_memo* m = &table[threads ? 1 : 0][(reinterpret_cast<uintptr_t>(kernel) >> 4) % 32];
   if (!(m->kernel == kernel && m->smem == smem && m->threads == threads && m->device == device))
     { m->kernel = kernel; m->smem = smem; m->threads = threads; m->device = device; m->per_sm = -1; m->optin = false; }
   return m;
