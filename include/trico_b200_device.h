@@ -33,6 +33,13 @@ typedef struct tb200_ctx tb200_ctx;
 TB200_API tb200_ctx* tb200_ctx_create(int device, void* cuda_stream);
 TB200_API void tb200_ctx_destroy(tb200_ctx* ctx);
 TB200_API void* tb200_ctx_stream(tb200_ctx* ctx);
+TB200_API int tb200_ctx_device(tb200_ctx* ctx);
+/* cudaSetDevice(ctx's device) for the calling thread (streams, events and pinned memory created by
+ * the helpers below belong to the current device) */
+TB200_API int tb200_ctx_make_current(tb200_ctx* ctx);
+TB200_API int tb200_set_device(int device);
+/* frees the workspaces the context has grown (they are re-created on demand) */
+TB200_API void tb200_ctx_trim(tb200_ctx* ctx);
 TB200_API int tb200_ctx_sync(tb200_ctx* ctx);                 /* 1 ok, 0 CUDA error */
 TB200_API const char* tb200_last_error(void);                /* text of the last failure in this thread */
 /* Number of kernels launched through this context so far (bench.py's gpu_launches). */

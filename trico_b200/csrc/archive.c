@@ -56,9 +56,11 @@ typedef struct
   uint64_t* h_scalar;                    /* page-locked, 64 bytes */
   } worker;
 
-#define MAX_WORKERS 64
-static worker g_workers[MAX_WORKERS];
-static int g_nworkers = 0;
+/* workers are heap objects in a table that grows on demand (the reference puts no bound on the
+ * number of concurrently open archives); idle workers beyond KEEP_IDLE give their device memory back */
+static worker** g_workers = NULL;
+static int g_nworkers = 0, g_workers_cap = 0;
+#define KEEP_IDLE 8
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 
 static int env_device(void)
@@ -76,30 +78,57 @@ static worker* worker_acquire(void)
   worker* w = NULL;
   pthread_mutex_lock(&g_lock);
   for (int i = 0; i < g_nworkers; ++i)
-    if (!g_workers[i].busy) { w = &g_workers[i]; break; }
-  if (!w && g_nworkers < MAX_WORKERS)
+    if (!g_workers[i]->busy) { w = g_workers[i]; break; }
+  if (!w)
     {
-    tb200_ctx* ctx = tb200_ctx_create(env_device(), NULL);
+    if (g_nworkers == g_workers_cap)
+      {
+      const int cap = g_workers_cap ? 2 * g_workers_cap : 16;
+      worker** t = (worker**)realloc(g_workers, (size_t)cap * sizeof(worker*));
+      if (t) { g_workers = t; g_workers_cap = cap; }
+      }
+    tb200_ctx* ctx = g_nworkers < g_workers_cap ? tb200_ctx_create(env_device(), NULL) : NULL;
     if (ctx)
       {
-      w = &g_workers[g_nworkers];
-      memset(w, 0, sizeof(*w));
-      w->ctx = ctx;
-      w->d_scalar = (uint64_t*)tb200_device_alloc(64);
-      if (!w->d_scalar) { tb200_ctx_destroy(ctx); w = NULL; }
-      else ++g_nworkers;
+      w = (worker*)calloc(1, sizeof(worker));
+      if (w)
+        {
+        w->ctx = ctx;
+        w->d_scalar = (uint64_t*)tb200_device_alloc(64);
+        }
+      if (!w || !w->d_scalar) { tb200_ctx_destroy(ctx); free(w); w = NULL; }
+      else g_workers[g_nworkers++] = w;
       }
     if (!w) set_dev_err();
     }
-  else if (!w) set_err("too many concurrently open archives");
   if (w) w->busy = 1;
   pthread_mutex_unlock(&g_lock);
+  if (w) tb200_ctx_make_current(w->ctx);      /* streams, events and pinned buffers created from here on belong to its device */
   return w;
+  }
+
+static void worker_trim(worker* w)
+  { /* called with the worker still marked busy: nobody else can take it meanwhile */
+  tb200_ctx_make_current(w->ctx);
+  tb200_ctx_sync(w->ctx);
+  if (w->pipe_ready) { tb200_stream_sync(w->s_h2d); tb200_stream_sync(w->s_d2h); }
+  if (w->d_raw) tb200_device_free(w->d_raw);
+  if (w->d_enc) tb200_device_free(w->d_enc);
+  if (w->d_ring) tb200_device_free(w->d_ring);
+  if (w->d_table) tb200_device_free(w->d_table);
+  w->d_raw = w->d_enc = w->d_ring = w->d_table = NULL;
+  w->raw_cap = w->enc_cap = w->ring_cap = w->table_cap = 0;
+  tb200_ctx_trim(w->ctx);
   }
 
 static void worker_release(worker* w)
   {
   if (!w) return;
+  pthread_mutex_lock(&g_lock);
+  int idle = 0;
+  for (int i = 0; i < g_nworkers; ++i) if (!g_workers[i]->busy) ++idle;
+  pthread_mutex_unlock(&g_lock);
+  if (idle >= KEEP_IDLE) worker_trim(w);
   pthread_mutex_lock(&g_lock);
   w->busy = 0;
   pthread_mutex_unlock(&g_lock);
@@ -145,6 +174,7 @@ static hostbuf hostbuf_get(uint64_t need)
   const uint64_t cap = need ? need : 1;
   if (tb200_device_count() > 0 && cap >= (64u << 10))
     {
+    tb200_set_device(env_device());          /* page-locking creates a context on the CURRENT device: not on GPU 0 for every rank */
     b.p = (uint8_t*)tb200_host_alloc_pinned(cap);
     b.pinned = b.p != NULL;
     }
@@ -623,6 +653,7 @@ static uint32_t peek_count(void* h, unsigned long long typemask)
   {
   archive* a = (archive*)h;
   if (!a || a->writable) return 0;
+  if (a->next_type < 1 || a->next_type > 20) return 0;       /* the type byte is untrusted: no shift by it */
   if (!((typemask >> a->next_type) & 1ull)) return 0;
   uint8_t b[4];
   if (!fetch(a, a->pos, b, 4)) return 0;
@@ -698,9 +729,15 @@ static int read_stream(void* h, int type, void** out, int alloc_result)
     {
     head[0] = (uint8_t)type;
     if (!fetch(a, a->pos + 4, head + 5, TB200_V1_FIXED_BYTES - 5)) return 0;
+    /* untrusted header fields: the chunk size first (it is a shift count), then the table and the
+     * payload against the bytes that are really there, in subtraction form so nothing wraps */
+    if (head[6] < 5 || head[6] > 15) { set_err("bad chunk size in stream header"); return 0; }
     const uint64_t nch = tb200_v1_nchunks(type, count, head[6]);
-    end = start + TB200_V1_FIXED_BYTES + 2 * nch + get64(head + 7);
-    if (end > a->data_size || end < start) return 0;
+    const uint64_t total = get64(head + 7);
+    const uint64_t left = a->data_size - start;                 /* >= TB200_V1_FIXED_BYTES: the header was fetched */
+    if (nch > (left - TB200_V1_FIXED_BYTES) / 2) return 0;     /* trico.c:71 */
+    if (total > left - TB200_V1_FIXED_BYTES - 2 * nch) return 0;
+    end = start + TB200_V1_FIXED_BYTES + 2 * nch + total;
     }
 
   if (out != NULL && raw_bytes > 0)

@@ -82,6 +82,19 @@ extern "C" void tb200_ctx_destroy(tb200_ctx* c)
   }
 
 extern "C" void* tb200_ctx_stream(tb200_ctx* c) { return (void*)c->stream; }
+extern "C" int tb200_ctx_device(tb200_ctx* c) { return c->device; }
+extern "C" int tb200_ctx_make_current(tb200_ctx* c) { CK(cudaSetDevice(c->device)); return 1; }
+extern "C" int tb200_set_device(int device) { CK(cudaSetDevice(device)); return 1; }
+// returns the device buffers a context grew to the driver (idle workers of the archive layer)
+extern "C" void tb200_ctx_trim(tb200_ctx* c)
+  {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->ws) cudaFree(c->ws);
+  if (c->big) cudaFree(c->big);
+  c->ws = nullptr; c->ws_bytes = 0; c->big = nullptr; c->big_bytes = 0;
+  }
 extern "C" uint64_t tb200_ctx_launch_count(tb200_ctx* c) { return c->launches; }
 
 extern "C" int tb200_ctx_sync(tb200_ctx* c)
@@ -129,15 +142,24 @@ static int big_prepare(tb200_ctx* c, size_t need, uint8_t** out)
   }
 
 // Per-launch host work that does not change from call to call - the shared-memory opt-in, the
-// occupancy query - is remembered per (kernel, shared memory size, threads, device): streams of a
-// few hundred kilobytes are launch-overhead bound.
-struct launch_memo { const void* kernel; size_t smem; int threads, device, per_sm, sms; bool optin; };
+// occupancy query - is remembered: streams of a few hundred kilobytes are launch-overhead bound.
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is process-wide per (kernel, device), so the
+// opt-in is a process-global maximum behind a mutex and is only ever RAISED: two archives on two
+// threads that need different sizes of the same kernel (16 KiB index blocks, 8 KiB colour blocks)
+// can never lower each other's limit.  Only the occupancy query is memoised per thread.
+#include <mutex>
+struct optin_entry { const void* kernel; int device; size_t bytes; };
+static std::mutex g_optin_lock;
+static optin_entry g_optin[256];
+static int g_noptin = 0;
+
+struct launch_memo { const void* kernel; size_t smem; int threads, device, per_sm, sms; };
 static launch_memo* memo_for(const void* kernel, size_t smem, int threads, int device)
   {
-  static thread_local launch_memo table[2][32];            // [0] shared-memory opt-in (threads == 0), [1] occupancy
-  launch_memo* m = &table[threads ? 1 : 0][(reinterpret_cast<uintptr_t>(kernel) >> 4) % 32];
+  static thread_local launch_memo table[64];
+  launch_memo* m = &table[((reinterpret_cast<uintptr_t>(kernel) >> 4) ^ (smem >> 8)) % 64];
   if (!(m->kernel == kernel && m->smem == smem && m->threads == threads && m->device == device))
-    { m->kernel = kernel; m->smem = smem; m->threads = threads; m->device = device; m->per_sm = -1; m->optin = false; }
+    { m->kernel = kernel; m->smem = smem; m->threads = threads; m->device = device; m->per_sm = -1; }
   return m;
   }
 
@@ -145,11 +167,16 @@ template <typename K>
 static int set_smem(K kernel, size_t bytes, const tb200_ctx* c)
   {
   if (bytes > (size_t)c->max_smem_optin) return fail_msg("kernel needs more shared memory than the device offers");
-  launch_memo* m = memo_for(reinterpret_cast<const void*>(kernel), bytes, 0, c->device);
-  if (m->optin) return 1;
   // (static + dynamic) above 48 KiB needs the opt-in; the kernels carry up to ~2 KiB of static shared memory
-  if (bytes > 40 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  m->optin = true;
+  if (bytes <= 40 * 1024) return 1;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  std::lock_guard<std::mutex> guard(g_optin_lock);
+  optin_entry* e = nullptr;
+  for (int i = 0; i < g_noptin; ++i) if (g_optin[i].kernel == key && g_optin[i].device == c->device) { e = &g_optin[i]; break; }
+  if (e && e->bytes >= bytes) return 1;
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (!e && g_noptin < 256) { e = &g_optin[g_noptin++]; e->kernel = key; e->device = c->device; }
+  if (e) e->bytes = bytes;          // table full: the attribute is simply set again next time
   return 1;
   }
 
