@@ -165,20 +165,38 @@ __device__ __forceinline__ uint32_t lz4_emit_run(DstPtr dst, uint32_t n, uint32_
 #define TB200_LZ4_DENSE_SEQ 24u        // bytes per sequence below which a block counts as dense (0: never)
 #endif
 constexpr uint32_t LZ4_SRC_PAD = 576;    // zeroed bytes the compressor may read past the block end (512-byte match extension steps)
+constexpr uint32_t LZ4_ENC_STAGE = 128;  // per-warp staging bytes for the sequences of one window (lz4_compress_warp)
+constexpr uint32_t LZ4_WIN_CAP = 36;     // match lengths are measured up to this inside a window; longer ones take the warp-wide extension
 
 // Compresses src[0..n) (shared memory, LZ4_SRC_PAD zero bytes readable past n) into dst.
-// `table` = (1 << HLOG) u16 entries of shared memory private to the warp.  n <= 65535.
-// Greedy single-pass matcher; every lane tests one position per step.  Like the reference
-// (lz4.c:879-909) the scan accelerates over data that does not match: after every 64 failed
-// attempts the distance between tested positions grows by one.
+// `table` = (1 << HLOG) u16 entries, `stage` = LZ4_ENC_STAGE bytes of shared memory private to
+// the warp.  n <= 65535.
+//
+// Greedy single-pass matcher in the spirit of LZ4_compress_generic (lz4.c:793-1181); every lane
+// tests one position per step.  Like the reference (lz4.c:879-909) the scan accelerates over data
+// that does not match: after every 64 failed attempts the distance between tested positions grows.
+//
+// Dense scan (stride 1: 32 consecutive positions per step).  A step does not stop at its first
+// match: every lane measures its own match (two candidates: the hash table's and the nearest
+// earlier lane of the window holding the same four bytes - the longer one wins) up to LZ4_WIN_CAP
+// bytes, a walk over the window picks the matches a left-to-right parse takes (with one position of
+// look-ahead: a longer match starting one byte later is preferred, as in lz4hc's lazy evaluation),
+// and ALL of them are emitted by their own lanes in one go through `stage`.  Data made of many
+// short sequences (real index planes, colour planes, attribute lists) thus costs one step per 32+
+// input bytes instead of one step per sequence.  A first match that reaches the cap (or sits
+// behind a long literal run) takes the warp-cooperative path: backward extension, 128 + 512 bytes
+// per step forward extension, one-store emission.
+// Table inserts follow the reference: literal positions and match starts, not match interiors
+// (lz4.c:1118 adds one position near the end of a match) - the interior positions of a run would
+// replace the candidate at the run's start, which is the one that extends across the run.
 template <int HLOG, typename DstPtr>
-__device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* table, unsigned long long* dbg = nullptr)
+__device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* table, uint8_t* stage, unsigned long long* dbg = nullptr)
   {
 #define TB200_EPH(i) do { if (dbg) { const long long t__ = clock64(); acc_ph[i] += (uint32_t)(t__ - t_ph); t_ph = t__; } } while (0)
   long long t_ph = dbg ? clock64() : 0;
   uint32_t acc_ph[5] = {0, 0, 0, 0, 0};
   const unsigned lane = lane_id();
-  const unsigned gt = lanemask_gt(), lt = lanemask_lt();
+  const unsigned lt = lanemask_lt();
   uint32_t op = 0, anchor = 0;
   if (n >= LZ4_MFLIMIT + 1)
     {
@@ -189,12 +207,26 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
     uint32_t p = 0, attempts = 0, nseq = 0;
     // Dense mode: data that yields a match every few bytes WITHOUT getting smaller for it (noisy
     // planes: colours, quantised heights - four equal bytes turn up by chance all the time) pays
-    // for every sequence twice, in this warp's serial parse and in the decoder's.  Once the
-    // sequences of the block average less than TB200_LZ4_DENSE_SEQ bytes and the output so far is
-    // above 90 % of the input, a match has to be 8 bytes long to be taken; failures accelerate the
-    // scan as usual.  (Blocks that do compress with short matches - small meshes' index planes -
-    // never get here.)
+    // for every sequence twice, here and in the decoder.  Once the sequences of the block average
+    // less than TB200_LZ4_DENSE_SEQ bytes and the output so far is above 90 % of the input, a
+    // match has to be 8 bytes long to be taken.  (Blocks that do compress with short matches -
+    // index planes of real meshes - never get here.)
     bool dense = false;
+    // Deterministic insert of the lanes flagged `ins` (position q, bucket h): every lane stores, then
+    // the losers of a bucket (they read back a lower position) store again - the highest position wins.
+    auto insert = [&](bool ins, uint32_t h, uint32_t q)
+      {
+      __syncwarp();
+      if (ins) table[h] = (uint16_t)q;
+      __syncwarp();
+      for (;;)
+        {
+        const bool lost = ins && table[h] < (uint16_t)q;
+        if (!__any_sync(FULL, lost)) break;
+        if (lost) table[h] = (uint16_t)q;
+        __syncwarp();
+        }
+      };
     while (p <= mflimit)
       {
       const uint32_t stride = 1u + (attempts >> 6);
@@ -210,12 +242,7 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
         const uint32_t ha = (sa * 2654435761u) >> (32 - HLOG), hb = (sb * 2654435761u) >> (32 - HLOG);
         const uint32_t ca = table[ha], cb = table[hb];
         const uint32_t ra = smem_read32(src, ca), rb = smem_read32(src, cb);     // table entries are positions inside the block
-        bool oka = va && ca < qa && ra == sa, okb = vb && cb < qb && rb == sb;
-        if (dense)
-          {
-          oka = oka && smem_read32(src, ca + 4) == smem_read32(src, qa + 4);
-          okb = okb && smem_read32(src, cb + 4) == smem_read32(src, qb + 4);
-          }
+        const bool oka = va && ca < qa && ra == sa, okb = vb && cb < qb && rb == sb;
         const unsigned maska = __ballot_sync(FULL, oka), maskb = __ballot_sync(FULL, okb);
         const int fa = maska ? __ffs((int)maska) - 1 : 32, fb = maska ? -1 : (maskb ? __ffs((int)maskb) - 1 : 32);
         // insert the positions up to the chosen match; the highest position of a bucket wins
@@ -239,49 +266,190 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
         mq = (maska ? p : p + 32u * stride) + (uint32_t)f * stride;
         mc = __shfl_sync(FULL, maska ? ca : cb, f);
         }
+      else if (stride >= 2u)
+        { // accelerated, one position per lane (the odd steps of the schedule above)
+        const uint32_t q = p + lane * stride;
+        const bool valid = q <= mflimit;
+        const uint32_t seq = valid ? smem_read32(src, q) : 0u;
+        const uint32_t h = (seq * 2654435761u) >> (32 - HLOG);
+        const uint32_t cand = table[h];
+        const bool ok = valid && cand < q && smem_read32(src, cand) == seq;
+        const unsigned mask = __ballot_sync(FULL, ok);
+        const int f = mask ? __ffs((int)mask) - 1 : 31;
+        insert(valid && (int)lane <= f, h, q);
+        if (mask == 0) { p += 32u * stride; attempts += 32; TB200_EPH(0); continue; }
+        mq = p + (uint32_t)f * stride;
+        mc = __shfl_sync(FULL, cand, f);
+        }
       else
-        {
-      const uint32_t q = p + lane * stride;
-      const bool valid = q <= mflimit;
-      const uint32_t seq = valid ? smem_read32(src, q) : 0u;
-      const uint32_t h = (seq * 2654435761u) >> (32 - HLOG);
-      uint32_t cand = table[h];
-      bool ok = valid && cand < q && smem_read32(src, cand) == seq;
-      // Repeats inside the window are invisible to the table (it is read before this window is
-      // inserted): find them by comparing the 4-byte sequences of the lanes directly.  Only while
-      // the scan is dense: once it accelerates (nothing matched for 64 positions) the data is not
-      // periodic at this scale, and match.any over 32 distinct values is the slowest instruction here.
-      if (stride == 1u)
-        {
+        { // ---- dense scan: positions p .. p+31 ----
+        const uint32_t q = p + lane;
+        const bool valid = q <= mflimit;
+        const uint32_t seq = valid ? smem_read32(src, q) : 0u;
+        const uint32_t h = (seq * 2654435761u) >> (32 - HLOG);
+        const uint32_t c1 = table[h];                                              // candidate 1: the table's
+        bool run1 = valid && c1 < q && smem_read32(src, c1) == seq;
+        // candidate 2: the nearest earlier lane of the window with the same four bytes (the table is
+        // read before this window is inserted, so repeats inside the window are invisible to it)
         const unsigned twins = __match_any_sync(FULL, valid ? seq : (0x5a000000u ^ lane)) & lt & __ballot_sync(FULL, valid);
-        if (valid && twins)
+        const uint32_t c2 = p + (31u - (uint32_t)__clz((int)(twins | 1u)));
+        bool run2 = valid && twins != 0;
+        const unsigned anyok = __ballot_sync(FULL, run1 || run2);
+        if (anyok == 0)
           {
-          const uint32_t near = p + (31u - (uint32_t)__clz((int)twins));
-          if (!ok || near > cand) { cand = near; ok = true; }
+          insert(valid, h, q);
+          p += 32u; attempts += 32; TB200_EPH(0);
+          continue;
           }
+        // Long-match data (runs, periodic index planes) must not pay for the window machinery: the
+        // first candidate of the window is measured by the whole warp (128 bytes in one step); if it
+        // reaches the cap it takes the warp-wide path at once.
+          {
+          const int f0 = __ffs((int)anyok) - 1;
+          const uint32_t c0 = __shfl_sync(FULL, run1 ? c1 : c2, f0);
+          const uint32_t q0 = p + (uint32_t)f0;
+          const uint32_t x = smem_read32(src, q0 + LZ4_MINMATCH + 4u * lane) ^ smem_read32(src, c0 + LZ4_MINMATCH + 4u * lane);
+          const unsigned ne = __ballot_sync(FULL, x != 0);
+          if (ne == 0 || 4u * ((uint32_t)__ffs((int)ne) - 1u) + LZ4_MINMATCH >= LZ4_WIN_CAP)
+            {
+            insert(valid && (int)lane <= f0, h, q);
+            mq = q0; mc = c0;
+            goto long_match;
+            }
+          }
+        // match lengths up to LZ4_WIN_CAP, four bytes per step, both candidates side by side
+        uint32_t l1 = run1 ? LZ4_MINMATCH : 0u, l2 = run2 ? LZ4_MINMATCH : 0u;
+#pragma unroll 1
+        for (uint32_t i = LZ4_MINMATCH; i < LZ4_WIN_CAP; i += 4)
+          {
+          const unsigned going = __ballot_sync(FULL, run1 || run2);
+          if (going == 0) break;
+          // every match of the window is still growing after 12 bytes: long-match data (runs, periodic
+          // index planes) - no point in measuring further, the first one takes the warp-wide path
+          if (i == 12u && going == anyok) break;
+          const uint32_t a = smem_read32(src, q + i);
+          if (run1)
+            {
+            const uint32_t x = a ^ smem_read32(src, c1 + i);
+            if (x) { l1 += ((uint32_t)__ffs((int)x) - 1u) >> 3; run1 = false; } else l1 += 4u;
+            }
+          if (run2)
+            {
+            const uint32_t x = a ^ smem_read32(src, c2 + i);
+            if (x) { l2 += ((uint32_t)__ffs((int)x) - 1u) >> 3; run2 = false; } else l2 += 4u;
+            }
+          }
+        // the better candidate: one that is still growing beats one that ended (the table's if both
+        // are: a far candidate that long is a real repeat, the near one a run); else the longer, the
+        // nearer on a tie
+        const bool take1 = run1 || (!run2 && l1 > l2);
+        uint32_t cand = take1 ? c1 : c2;
+        uint32_t L = take1 ? l1 : l2;
+        bool capped = take1 ? run1 : run2;
+        const uint32_t maxlen = matchlimit - (valid ? q : mflimit);               // >= 7
+        if (L >= maxlen) { L = maxlen; capped = false; }                           // ends at the last position a match may cover
+        const unsigned mask = __ballot_sync(FULL, L >= (dense ? 8u : LZ4_MINMATCH)), capmask = __ballot_sync(FULL, capped);
+        if (mask == 0)
+          { // (dense mode: nothing of 8+ bytes in this window)
+          insert(valid, h, q);
+          p += 32u; attempts += 32; TB200_EPH(0);
+          continue;
+          }
+        // walk over the window: the matches of a greedy left-to-right parse
+        unsigned sel = 0;
+        int longf = -1;
+          {
+          uint32_t cur = 0;
+          while (cur < 32u)
+            {
+            const unsigned m = mask & (0xffffffffu << cur);
+            if (m == 0) break;
+            const uint32_t f = (uint32_t)__ffs((int)m) - 1u;
+            const bool capf = (capmask >> f) & 1u;
+            const uint32_t Lf = __shfl_sync(FULL, L, f);
+            if (!capf && f < 31u && ((mask >> (f + 1u)) & 1u))
+              { // look-ahead: a longer match starts one byte later - position f becomes a literal
+              const uint32_t Ln = __shfl_sync(FULL, L, f + 1u);
+              if (((capmask >> (f + 1u)) & 1u) || Ln > Lf) { cur = f + 1u; continue; }
+              }
+            if (capf) { if (sel == 0) longf = (int)f; break; }
+            sel |= 1u << f;
+            cur = f + Lf;
+            }
+          }
+        if (sel != 0)
+          { // a first sequence behind a long literal run is emitted by the whole warp
+          const uint32_t f0 = (uint32_t)__ffs((int)sel) - 1u;
+          if (p + f0 - anchor >= 32u) { longf = (int)f0; sel = 0; }
+          }
+        attempts = 0;
+        if (sel != 0)
+          { // ---- all sequences of the window at once ----
+          const bool chosen = (sel >> lane) & 1u;
+          const uint32_t e_rel = lane + L;                                         // end of this lane's match, relative to p
+          const unsigned below = sel & lt;
+          const int jprev = below ? 31 - __clz((int)below) : 0;
+          int prev_end = __shfl_sync(FULL, (int)e_rel, jprev);
+          if (!below) prev_end = (int)anchor - (int)p;                             // <= 0: literals pending from before the window
+          uint32_t lit = chosen ? (uint32_t)((int)lane - prev_end) : 0u;
+          uint32_t mqi = q, mci = cand, Li = L;
+          if (chosen)                                                              // backward extension over this sequence's own literals (lz4.c:947-950)
+            while (lit > 0u && mci > 0u && src[mqi - 1u] == src[mci - 1u]) { --mqi; --mci; ++Li; --lit; }
+          const uint32_t mcode = Li - LZ4_MINMATCH;
+          uint32_t size = 0;
+          if (chosen) size = 1u + lit + (lit >= 15u ? (lit - 15u) / 255u + 1u : 0u) + 2u + (mcode >= 15u ? (mcode - 15u) / 255u + 1u : 0u);
+          uint32_t incl = size;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+            {
+            const uint32_t up = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (unsigned)o) incl += up;
+            }
+          // the sequences that fit into the staging buffer (a prefix of the chosen ones; the first always does)
+          const unsigned kept = sel & __ballot_sync(FULL, incl <= LZ4_ENC_STAGE);
+          const int lastk = 31 - __clz((int)kept);
+          const uint32_t total = __shfl_sync(FULL, incl, lastk);
+          const uint32_t end_rel = __shfl_sync(FULL, e_rel, lastk);
+          if ((kept >> lane) & 1u)
+            {
+            uint8_t* o = stage + (incl - size);
+            uint32_t k = 0;
+            o[k++] = (uint8_t)(((lit >= 15u ? 15u : lit) << 4) | (mcode >= 15u ? 15u : mcode));
+            if (lit >= 15u) { uint32_t r = lit - 15u; while (r >= 255u) { o[k++] = 255; r -= 255u; } o[k++] = (uint8_t)r; }
+            for (uint32_t j = 0; j < lit; ++j) o[k + j] = src[mqi - lit + j];
+            k += lit;
+            const uint32_t offv = mqi - mci;
+            o[k++] = (uint8_t)offv; o[k++] = (uint8_t)(offv >> 8);
+            if (mcode >= 15u) { uint32_t r = mcode - 15u; while (r >= 255u) { o[k++] = 255; r -= 255u; } o[k++] = (uint8_t)r; }
+            }
+          __syncwarp();
+          for (uint32_t i = lane; i < total; i += 32) dst[op + i] = stage[i];
+          op += total;
+          // next scan position: behind the last sequence, or behind the window if nothing else in it matched
+          const unsigned rest = end_rel < 32u ? (mask & (0xffffffffu << end_rel)) : 0u;
+          const uint32_t pnew = (end_rel < 32u && rest == 0) ? p + 32u : p + end_rel;
+          // inserts: scanned positions that are not inside a match
+          const unsigned atbelow = kept & (lt | (1u << lane));
+          const int js = atbelow ? 31 - __clz((int)atbelow) : 0;
+          const uint32_t endjs = __shfl_sync(FULL, e_rel, js);
+          const bool inside = atbelow != 0 && lane > (unsigned)js && lane < endjs;
+          insert(valid && q < pnew && !inside, h, q);
+          // like lz4.c:1118, remember one position inside the tail of a match that left the window
+          if (end_rel > 32u && lane == 0 && pnew - 2u <= mflimit) table[(smem_read32(src, pnew - 2u) * 2654435761u) >> (32 - HLOG)] = (uint16_t)(pnew - 2u);
+          __syncwarp();
+          anchor = p + end_rel;
+          p = pnew;
+          nseq += (uint32_t)__popc(kept);
+          dense = TB200_LZ4_DENSE_SEQ != 0u && anchor >= TB200_LZ4_DENSE_MIN && nseq * TB200_LZ4_DENSE_SEQ > anchor && 10u * op > 9u * anchor;
+          TB200_EPH(1);
+          continue;
+          }
+        // a long first match
+        insert(valid && (int)lane <= longf, h, q);
+        mq = p + (uint32_t)longf;
+        mc = __shfl_sync(FULL, cand, longf);
         }
-      if (dense) ok = ok && smem_read32(src, cand + 4) == smem_read32(src, q + 4);
-      const unsigned mask = __ballot_sync(FULL, ok);
-      const int f = mask ? __ffs((int)mask) - 1 : 31;
-      // Insert the tested positions up to the chosen match only: later ones are scanned again
-      // and must still see their older candidates.  Among lanes sharing a bucket the highest
-      // position must win, so that the table (and the output) is deterministic: every lane
-      // stores, then the losers of a bucket (they read back a lower position) store again.
-      const bool ins = valid && (int)lane <= f;
-      __syncwarp();
-      if (ins) table[h] = (uint16_t)q;
-      __syncwarp();
-      for (;;)
-        {
-        const bool lost = ins && table[h] < (uint16_t)q;
-        if (!__any_sync(FULL, lost)) break;
-        if (lost) table[h] = (uint16_t)q;
-        __syncwarp();
-        }
-      if (mask == 0) { p += 32u * stride; attempts += 32; TB200_EPH(0); continue; }
-      mq = p + (uint32_t)f * stride;
-      mc = __shfl_sync(FULL, cand, f);
-        }
+long_match:
       attempts = 0;
       TB200_EPH(1);
       // backward extension over bytes not yet emitted (lz4.c:947-950 does the same serially)
@@ -330,7 +498,7 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
       op = lz4_emit(dst, op, src, anchor, mq - anchor, mq - mc, len);
       p = anchor = mq + len;
       ++nseq;
-      dense = p >= TB200_LZ4_DENSE_MIN && nseq * TB200_LZ4_DENSE_SEQ > p && 10u * op > 9u * p;
+      dense = TB200_LZ4_DENSE_SEQ != 0u && p >= TB200_LZ4_DENSE_MIN && nseq * TB200_LZ4_DENSE_SEQ > p && 10u * op > 9u * p;
       // like lz4.c:1118, remember one position inside the match tail
       if (lane == 0 && p - 2 <= mflimit) table[(smem_read32(src, p - 2) * 2654435761u) >> (32 - HLOG)] = (uint16_t)(p - 2);
       __syncwarp();
@@ -551,6 +719,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
   uint8_t* buf = smem_raw + (size_t)warp * pstride;
   uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw + (size_t)WARPS * pstride) + ((size_t)warp << HLOG);
+  uint8_t* stage = smem_raw + (size_t)WARPS * pstride + ((size_t)WARPS << HLOG) * sizeof(uint16_t) + (size_t)warp * LZ4_ENC_STAGE;
 
   // A ticket is one HALF of the planes of a range of B elements - the even or the odd ones - which
   // the warp compresses one after the other.  (The two halves are taken by two warps at about the
@@ -666,7 +835,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
         if (a.dbg && lane == 0) { const long long t2 = clock64(); atomicAdd(a.dbg + (p & 7), (unsigned long long)(t2 - t_ph)); t_ph = t2; }
 
         // 2. compress into this chunk's slot
-        nbytes = lz4_compress_warp<HLOG>(buf, cnt, a.scratch + g * a.slot, table, a.dbg ? a.dbg + 16 + 8 * (p & 7) : nullptr);
+        nbytes = lz4_compress_warp<HLOG>(buf, cnt, a.scratch + g * a.slot, table, stage, a.dbg ? a.dbg + 16 + 8 * (p & 7) : nullptr);
         }
       if (a.dbg && lane == 0) { const long long t2 = clock64(); atomicAdd(a.dbg + 8 + (p & 7), (unsigned long long)(t2 - t_ph)); }
       if (lane == 0)
@@ -945,6 +1114,111 @@ __device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint3
     }
   }
 
+// Up to 32 consecutive SHORT sequences at once (literal run < 15, match <= LZ4_BATCH_MAXMATCH):
+// the regime of real index planes, colour planes and attribute lists, where a sequence is a few
+// bytes and the one-sequence-per-iteration loop below pays ~1000 cycles for each.
+//   1. a walk over the tokens (one shared-memory read per sequence on the dependency chain, every
+//      lane runs it; lane k keeps sequence k)
+//   2. every lane fetches its own literals and offset, then writes the literals - all input is read
+//      before anything is written: the output of a later sequence may cover the (consumed) input of
+//      an earlier one, in-place margin or not
+//   3. the matches, every lane its own, in rounds: a match is copied once everything below the
+//      end of its source is final, i.e. lies below the first match that is still open.  Far matches
+//      (the common case) all go in the first round.
+// Returns the number of sequences done (0: the next one is not of this kind), -1 on a malformed one.
+constexpr uint32_t LZ4_BATCH_MAXMATCH = 64;
+__device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint32_t iend, uint32_t& op, uint32_t cap)
+  {
+  const unsigned lane = lane_id();
+  uint32_t sp = ip, o = op;
+  uint32_t my_sp = 0, my_op = 0, my_lit = 0, my_ml = 0;
+  int nseq = 0;
+#pragma unroll 1
+  for (int k = 0; k < 32; ++k)
+    {
+    if (sp >= iend) break;
+    const uint32_t t = buf[sp];
+    const uint32_t lit = t >> 4, mlc = t & 15u;
+    if (lit == 15u || sp + 3u + lit > iend) break;          // long literal run, or the block's last sequence (no match part)
+    uint32_t ml = LZ4_MINMATCH + mlc, adv = 3u + lit;
+    if (mlc == 15u)
+      {
+      const uint32_t x = buf[sp + adv];
+      if (x > LZ4_BATCH_MAXMATCH - 19u) break;              // long match (or a longer continuation)
+      ml += x; ++adv;
+      }
+    if ((int)lane == k) { my_sp = sp; my_op = o; my_lit = lit; my_ml = ml; }
+    sp += adv; o += lit + ml; ++nseq;
+    }
+  if (nseq == 0) return 0;
+  const bool act = (int)lane < nseq;
+  uint64_t lo = 0, hi = 0;
+  uint32_t off = 0;
+  if (act)
+    {
+    const uint32_t l0 = my_sp + 1u;
+    lo = (uint64_t)smem_read32(buf, l0);
+    if (my_lit > 4u) lo |= (uint64_t)smem_read32(buf, l0 + 4u) << 32;
+    if (my_lit > 8u) hi = (uint64_t)smem_read32(buf, l0 + 8u);
+    if (my_lit > 12u) hi |= (uint64_t)smem_read32(buf, l0 + 12u) << 32;
+    const uint32_t e = l0 + my_lit;
+    off = (uint32_t)buf[e] | ((uint32_t)buf[e + 1u] << 8);
+    }
+  const uint32_t dst = my_op + my_lit;
+  const bool fine = !act || (off != 0u && off <= dst && dst + my_ml <= cap);
+  if (!__all_sync(FULL, fine)) return -1;
+  __syncwarp();
+  if (act)
+    for (uint32_t j = 0; j < my_lit; ++j)
+      buf[my_op + j] = (uint8_t)((j < 8u ? lo >> (8u * j) : hi >> (8u * (j - 8u))) & 0xffu);
+  __syncwarp();
+  // the matches of earlier sequences this lane's source overlaps: [s, e) = the part of the source
+  // that this lane does not produce itself, against every earlier match [dst_j, dst_j + ml_j)
+  const uint32_t s_lo = dst - off, s_hi = act ? min(s_lo + my_ml, dst) : 0u;
+  unsigned waits = 0;
+  for (int j = 0; j < nseq - 1; ++j)
+    {
+    const uint32_t aj = __shfl_sync(FULL, dst, j), bj = aj + __shfl_sync(FULL, my_ml, j);
+    if ((int)lane > j && aj < s_hi && bj > s_lo) waits |= 1u << j;
+    }
+  bool open = act;
+  for (;;)
+    {
+    const unsigned und = __ballot_sync(FULL, open);
+    if (und == 0) break;
+    if (open && (und & waits) == 0)
+      {
+      const uint8_t* ms = buf + dst - off;
+      uint8_t* md = buf + dst;
+      if (off >= 4u)
+        { // four bytes per step: the loads of a step lie before its first store
+        for (uint32_t j = 0; j < my_ml; j += 4u)
+          {
+          const uint32_t b0 = ms[j], b1 = ms[j + 1u], b2 = ms[j + 2u], b3 = ms[j + 3u];
+          md[j] = (uint8_t)b0;
+          if (j + 1u < my_ml) md[j + 1u] = (uint8_t)b1;
+          if (j + 2u < my_ml) md[j + 2u] = (uint8_t)b2;
+          if (j + 3u < my_ml) md[j + 3u] = (uint8_t)b3;
+          }
+        }
+      else
+        { // period 1..3: the pattern comes from a register
+        const uint32_t pat = (uint32_t)ms[0] | ((uint32_t)ms[off > 1u ? 1 : 0] << 8) | ((uint32_t)ms[off > 2u ? 2 : 0] << 16);
+        uint32_t idx = 0;
+        for (uint32_t j = 0; j < my_ml; ++j)
+          {
+          md[j] = (uint8_t)(pat >> (8u * idx));
+          idx = (idx + 1u == off) ? 0u : idx + 1u;
+          }
+        }
+      open = false;
+      }
+    __syncwarp();
+    }
+  ip = sp; op = o;
+  return nseq;
+  }
+
 // Decodes the block buf[ip, iend) into buf[0, cap).  Returns the bytes produced or 0xffffffff.
 // One sequence per iteration, every step warp-wide.  A lone warp issues one dependent instruction
 // every ~6 cycles, so the loop is written for instruction count: the token and the 31 bytes behind
@@ -966,8 +1240,16 @@ __device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip
   // window of the NEXT sequence is requested as soon as its position is known, before the match of
   // the current one is produced
   uint32_t b = buf[ip + lane];
+  bool batching = false;                        // the last sequence was a short one: try the batch decoder
   for (;;)
     {
+    if (batching)
+      {
+      const int nb = lz4_decode_batch(buf, ip, iend, op, cap);
+      if (nb < 0) return 0xffffffffu;
+      if (nb < 4) batching = false;
+      if (nb > 0) { __syncwarp(); b = buf[ip + lane]; continue; }
+      }
     const uint32_t token = __shfl_sync(FULL, b, 0);
     uint32_t lit = token >> 4, ml = token & 15u, offset;
     const bool short_lit = lit < 15u;
@@ -1043,6 +1325,7 @@ __device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip
       }
     op += mlen;
     b = bnext;
+    batching = short_lit && mlen <= 32u;
     __syncwarp();
     }
   return op;
