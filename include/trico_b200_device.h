@@ -105,6 +105,29 @@ TB200_API int tb200_encode_stream(tb200_ctx* ctx, int type, const void* d_data, 
  * bytes (starting at the type byte) are on the device at d_stream. */
 TB200_API int tb200_decode_stream(tb200_ctx* ctx, const uint8_t* header, const uint8_t* d_stream, uint64_t stream_bytes, void* d_out);
 
+/* ---- multi-GPU: chunk-sharded streams; one process per GPU, NCCL loaded at run time ----
+ * A stream is cut into contiguous chunk-aligned shares, one per rank.  Every rank encodes its share
+ * with the ordinary kernels (no data-path collective); an all-gather exchanges the compressed sizes;
+ * optionally the shares are moved device to device to their final offsets on the root (grouped
+ * ncclSend / ncclRecv).  The assembled stream is byte-identical to tb200_encode_stream on one GPU. */
+typedef struct tb200_comm tb200_comm;
+TB200_API int tb200_comm_unique_id(uint8_t* id128);                 /* rank 0 creates it, the host distributes the 128 bytes */
+TB200_API tb200_comm* tb200_comm_create(tb200_ctx* ctx, int rank, int world, const uint8_t* id128);
+TB200_API void tb200_comm_destroy(tb200_comm* comm);
+TB200_API int tb200_comm_rank(tb200_comm* comm);
+TB200_API int tb200_comm_world(tb200_comm* comm);
+/* share of `rank`: units [*first, *first + *n) of a stream of `count` units (vertices, triangles, ...) */
+TB200_API int tb200_shard_range(int type, uint32_t count, int log2_chunk, int rank, int world, uint32_t* first, uint32_t* n);
+/* collective; see device_api_comm.inc.  ms (may be NULL): [0] encode + size exchange, [1] assembly, device time */
+TB200_API int tb200_encode_stream_sharded(tb200_ctx* ctx, tb200_comm* comm, int type, const void* d_local, uint32_t count_local,
+                        uint32_t count_total, int log2_chunk, int root, int assemble,
+                        uint8_t* d_out, uint64_t out_cap, uint64_t* d_stream_bytes, float* ms);
+/* this rank's encoded share of the last sharded call (size table, payload): device pointers valid until the next call */
+TB200_API int tb200_comm_local_share(tb200_comm* comm, const uint8_t** d_sizes, uint64_t* table_bytes, const uint8_t** d_payload, uint64_t* payload_bytes);
+/* decodes units [first, first + n) of a whole v1 stream: what a rank does with the chunk range it is handed */
+TB200_API int tb200_decode_stream_range(tb200_ctx* ctx, const uint8_t* header, const uint8_t* d_stream, uint64_t stream_bytes,
+                        uint32_t first, uint32_t n, void* d_out);
+
 /* ---- standalone transposes (the 14 exported trico_transpose_* symbols) ---- */
 TB200_API int tb200_deinterleave(tb200_ctx* ctx, int wordsize, int ncomp, const void* d_aos, uint64_t n, void* const* d_comp);
 TB200_API int tb200_interleave(tb200_ctx* ctx, int wordsize, int ncomp, void* d_aos, uint64_t n, const void* const* d_comp);

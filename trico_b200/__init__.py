@@ -77,6 +77,13 @@ def load() -> C.CDLL:
         "tb200_event_record": (C.c_int, [_vp, _vp]),
         "tb200_event_elapsed_ms": (C.c_float, [_vp, _vp]),
         "trico_b200_last_error": (C.c_char_p, []),
+        "tb200_comm_unique_id": (C.c_int, [_vp]),
+        "tb200_comm_create": (_vp, [_vp, C.c_int, C.c_int, _vp]),
+        "tb200_comm_destroy": (None, [_vp]),
+        "tb200_shard_range": (C.c_int, [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+        "tb200_encode_stream_sharded": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, _vp, C.POINTER(C.c_float)]),
+        "tb200_comm_local_share": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(C.c_uint64)]),
+        "tb200_decode_stream_range": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -186,6 +193,48 @@ class Device:
         for b in (d_in, d_out, d_sz):
             b.free()
         return out
+
+    # -- multi-GPU: chunk-sharded streams (one process per GPU) -------------------------------
+    def shard_range(self, stream_type: int, count: int, rank: int, world: int, log2_chunk: int = 0):
+        """-> (first, n): the units of a stream of `count` units that belong to `rank`"""
+        f, n = C.c_uint32(0), C.c_uint32(0)
+        self._ck(self.lib.tb200_shard_range(stream_type, count, log2_chunk, rank, world, C.byref(f), C.byref(n)))
+        return f.value, n.value
+
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._ck(self.lib.tb200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_create(self, rank: int, world: int, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        comm = self.lib.tb200_comm_create(self.ctx, rank, world, buf)
+        if not comm:
+            raise TB200Error(self.lib.tb200_last_error().decode())
+        return comm
+
+    def comm_destroy(self, comm):
+        self.lib.tb200_comm_destroy(comm)
+
+    def encode_stream_sharded(self, comm, stream_type: int, d_local: int, count_local: int, count_total: int, root: int = 0,
+                              assemble: bool = True, d_out: int = 0, out_cap: int = 0, d_bytes: int = 0, log2_chunk: int = 0, timed: bool = True):
+        """collective; -> (ms_encode_and_exchange, ms_assemble) when timed"""
+        ms = (C.c_float * 2)()
+        self._ck(self.lib.tb200_encode_stream_sharded(self.ctx, comm, stream_type, _vp(d_local), count_local, count_total, log2_chunk, root,
+                                                      1 if assemble else 0, _vp(d_out) if d_out else None, out_cap,
+                                                      _vp(d_bytes) if d_bytes else None, ms if timed else None))
+        return float(ms[0]), float(ms[1])
+
+    def comm_local_share(self, comm):
+        """-> (d_sizes, table_bytes, d_payload, payload_bytes) of this rank's share of the last sharded call"""
+        ps, pp = _vp(), _vp()
+        ts, pb = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.lib.tb200_comm_local_share(comm, C.byref(ps), C.byref(ts), C.byref(pp), C.byref(pb)))
+        return ps.value, ts.value, pp.value, pb.value
+
+    def decode_stream_range(self, header: bytes, d_stream: int, stream_bytes: int, first: int, n: int, d_out: int):
+        hb = (C.c_uint8 * 15).from_buffer_copy(header[:15])
+        self._ck(self.lib.tb200_decode_stream_range(self.ctx, hb, _vp(d_stream), stream_bytes, first, n, _vp(d_out)))
 
     def decode_stream(self, stream: bytes) -> np.ndarray:
         """v1 stream bytes -> flat host array of the stream's scalars."""

@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmds = [
         [os.environ.get("CC", "gcc"), *CC_FLAGS, *inc, "-c", os.path.join(CSRC, "archive.c"), "-o", obj_c],
         [nvcc, *NVCC_FLAGS, *inc, "-c", os.path.join(CSRC, "device_api.cu"), "-o", obj_cu],
-        [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, obj_c, obj_cu, "-lcudart"],
+        [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, obj_c, obj_cu, "-lcudart", "-ldl"],
     ]
     for cmd in cmds:
         if verbose:
@@ -84,7 +84,7 @@ def build_variant(name: str, defs, verbose: bool = False) -> str:
     cmds = [
         [os.environ.get("CC", "gcc"), *CC_FLAGS, *inc, "-c", os.path.join(CSRC, "archive.c"), "-o", obj_c],
         [nvcc, *NVCC_FLAGS, *dd, *inc, "-c", os.path.join(CSRC, "device_api.cu"), "-o", obj_cu],
-        [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, obj_c, obj_cu, "-lcudart"],
+        [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, obj_c, obj_cu, "-lcudart", "-ldl"],
     ]
     for cmd in cmds:
         if verbose:

@@ -466,3 +466,4 @@ extern "C" int tb200_fpc_decode_v0(tb200_ctx* c, int wordsize, const uint8_t* d_
 
 #include "device_api_lz4.inc"
 #include "device_api_misc.inc"
+#include "device_api_comm.inc"

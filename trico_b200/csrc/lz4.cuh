@@ -294,6 +294,12 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
         const unsigned twins = __match_any_sync(FULL, valid ? seq : (0x5a000000u ^ lane)) & lt & __ballot_sync(FULL, valid);
         const uint32_t c2 = p + (31u - (uint32_t)__clz((int)(twins | 1u)));
         bool run2 = valid && twins != 0;
+        if (dense)
+          { // noisy data: a candidate has to match 8 bytes to be looked at at all
+          const uint32_t nxt = smem_read32(src, q + 4u);
+          run1 = run1 && smem_read32(src, c1 + 4u) == nxt;
+          run2 = run2 && smem_read32(src, c2 + 4u) == nxt;
+          }
         const unsigned anyok = __ballot_sync(FULL, run1 || run2);
         if (anyok == 0)
           {
@@ -1114,7 +1120,7 @@ __device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint3
     }
   }
 
-// Up to 32 consecutive SHORT sequences at once (literal run < 15, match <= LZ4_BATCH_MAXMATCH):
+// Up to 32 consecutive SHORT sequences at once (literal run <= LZ4_BATCH_MAXLIT, match <= LZ4_BATCH_MAXMATCH):
 // the regime of real index planes, colour planes and attribute lists, where a sequence is a few
 // bytes and the one-sequence-per-iteration loop below pays ~1000 cycles for each.
 //   1. a walk over the tokens (one shared-memory read per sequence on the dependency chain, every
@@ -1127,6 +1133,7 @@ __device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint3
 //      (the common case) all go in the first round.
 // Returns the number of sequences done (0: the next one is not of this kind), -1 on a malformed one.
 constexpr uint32_t LZ4_BATCH_MAXMATCH = 64;
+constexpr uint32_t LZ4_BATCH_MAXLIT = 32;
 __device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint32_t iend, uint32_t& op, uint32_t cap)
   {
   const unsigned lane = lane_id();
@@ -1138,9 +1145,18 @@ __device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint
     {
     if (sp >= iend) break;
     const uint32_t t = buf[sp];
-    const uint32_t lit = t >> 4, mlc = t & 15u;
-    if (lit == 15u || sp + 3u + lit > iend) break;          // long literal run, or the block's last sequence (no match part)
-    uint32_t ml = LZ4_MINMATCH + mlc, adv = 3u + lit;
+    uint32_t lit = t >> 4;
+    const uint32_t mlc = t & 15u;
+    uint32_t adv = 3u;
+    if (lit == 15u)
+      {
+      const uint32_t x = buf[sp + 1u];
+      if (x > LZ4_BATCH_MAXLIT - 15u) break;                // long literal run
+      lit += x; ++adv;
+      }
+    adv += lit;
+    if (sp + adv > iend) break;                              // the block's last sequence (no match part)
+    uint32_t ml = LZ4_MINMATCH + mlc;
     if (mlc == 15u)
       {
       const uint32_t x = buf[sp + adv];
@@ -1152,15 +1168,17 @@ __device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint
     }
   if (nseq == 0) return 0;
   const bool act = (int)lane < nseq;
-  uint64_t lo = 0, hi = 0;
+  uint64_t lw[4] = {0, 0, 0, 0};                            // this lane's literals (<= 32 bytes)
   uint32_t off = 0;
   if (act)
     {
-    const uint32_t l0 = my_sp + 1u;
-    lo = (uint64_t)smem_read32(buf, l0);
-    if (my_lit > 4u) lo |= (uint64_t)smem_read32(buf, l0 + 4u) << 32;
-    if (my_lit > 8u) hi = (uint64_t)smem_read32(buf, l0 + 8u);
-    if (my_lit > 12u) hi |= (uint64_t)smem_read32(buf, l0 + 12u) << 32;
+    const uint32_t l0 = my_sp + (my_lit >= 15u ? 2u : 1u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      {
+      if (my_lit > 8u * u) lw[u] = (uint64_t)smem_read32(buf, l0 + 8u * u);
+      if (my_lit > 8u * u + 4u) lw[u] |= (uint64_t)smem_read32(buf, l0 + 8u * u + 4u) << 32;
+      }
     const uint32_t e = l0 + my_lit;
     off = (uint32_t)buf[e] | ((uint32_t)buf[e + 1u] << 8);
     }
@@ -1169,8 +1187,12 @@ __device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint
   if (!__all_sync(FULL, fine)) return -1;
   __syncwarp();
   if (act)
-    for (uint32_t j = 0; j < my_lit; ++j)
-      buf[my_op + j] = (uint8_t)((j < 8u ? lo >> (8u * j) : hi >> (8u * (j - 8u))) & 0xffu);
+    {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      for (uint32_t j = 8u * u; j < my_lit && j < 8u * u + 8u; ++j)
+        buf[my_op + j] = (uint8_t)(lw[u] >> (8u * (j - 8u * u)));
+    }
   __syncwarp();
   // the matches of earlier sequences this lane's source overlaps: [s, e) = the part of the source
   // that this lane does not produce itself, against every earlier match [dst_j, dst_j + ml_j)
@@ -1325,7 +1347,7 @@ __device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip
       }
     op += mlen;
     b = bnext;
-    batching = short_lit && mlen <= 32u;
+    batching = lit <= LZ4_BATCH_MAXLIT && mlen <= 32u;
     __syncwarp();
     }
   return op;

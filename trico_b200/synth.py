@@ -95,7 +95,7 @@ def colors_rgba(v: np.ndarray, seed: int = 0) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------ torch (GPU)
-def grid_mesh_torch(W: int, H: int, device, jitter: float = 1.0, seed: int = 0, double: bool = False, long_index: bool = False, shuffle: int = 64):
+def grid_mesh_torch(W: int, H: int, device, jitter: float = 1.0, seed: int = 0, double: bool = False, long_index: bool = False, shuffle: int = 64, triangles: bool = True):
     """Same mesh family generated on `device` with torch (bench sizes: 1e8 vertices in < 1 s).
     Not bit-identical to the numpy path (device sin/cos); both bench arms consume THESE arrays."""
     import torch
@@ -122,6 +122,8 @@ def grid_mesh_torch(W: int, H: int, device, jitter: float = 1.0, seed: int = 0, 
     pz = 5.0 * torch.sin(0.37 * px) * torch.cos(0.21 * py) + jitter * 0.01 * (u(k + 2) - 0.5)
     v = torch.stack([px, py, pz], dim=1).to(torch.float64 if double else torch.float32)
     del px, py, pz, x, y, k
+    if not triangles:                       # point cloud: no connectivity (and nothing to shuffle against)
+        return v.contiguous(), None
     xs = torch.arange(W - 1, dtype=torch.int64, device=device)
     ys = torch.arange(H - 1, dtype=torch.int64, device=device)
     c = (ys[:, None] * W + xs[None, :]).reshape(-1)
