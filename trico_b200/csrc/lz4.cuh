@@ -164,6 +164,9 @@ __device__ __forceinline__ uint32_t lz4_emit_run(DstPtr dst, uint32_t n, uint32_
 #ifndef TB200_LZ4_DENSE_SEQ
 #define TB200_LZ4_DENSE_SEQ 24u        // bytes per sequence below which a block counts as dense (0: never)
 #endif
+#ifndef TB200_LZ4_DENSE_OUT
+#define TB200_LZ4_DENSE_OUT 10u        // ... while the output stays above 8 / TB200_LZ4_DENSE_OUT of the input
+#endif
 constexpr uint32_t LZ4_SRC_PAD = 576;    // zeroed bytes the compressor may read past the block end (512-byte match extension steps)
 constexpr uint32_t LZ4_ENC_STAGE = 128;  // per-warp staging bytes for the sequences of one window (lz4_compress_warp)
 constexpr uint32_t LZ4_WIN_CAP = 36;     // match lengths are measured up to this inside a window; longer ones take the warp-wide extension
@@ -208,7 +211,7 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
     // Dense mode: data that yields a match every few bytes WITHOUT getting smaller for it (noisy
     // planes: colours, quantised heights - four equal bytes turn up by chance all the time) pays
     // for every sequence twice, here and in the decoder.  Once the sequences of the block average
-    // less than TB200_LZ4_DENSE_SEQ bytes and the output so far is above 90 % of the input, a
+    // less than TB200_LZ4_DENSE_SEQ bytes and the output so far is above 80 % of the input, a
     // match has to be 8 bytes long to be taken.  (Blocks that do compress with short matches -
     // index planes of real meshes - never get here.)
     bool dense = false;
@@ -446,7 +449,7 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
           anchor = p + end_rel;
           p = pnew;
           nseq += (uint32_t)__popc(kept);
-          dense = TB200_LZ4_DENSE_SEQ != 0u && anchor >= TB200_LZ4_DENSE_MIN && nseq * TB200_LZ4_DENSE_SEQ > anchor && 10u * op > 9u * anchor;
+          dense = TB200_LZ4_DENSE_SEQ != 0u && anchor >= TB200_LZ4_DENSE_MIN && nseq * TB200_LZ4_DENSE_SEQ > anchor && TB200_LZ4_DENSE_OUT * op > 8u * anchor;
           TB200_EPH(1);
           continue;
           }
@@ -504,7 +507,7 @@ long_match:
       op = lz4_emit(dst, op, src, anchor, mq - anchor, mq - mc, len);
       p = anchor = mq + len;
       ++nseq;
-      dense = TB200_LZ4_DENSE_SEQ != 0u && p >= TB200_LZ4_DENSE_MIN && nseq * TB200_LZ4_DENSE_SEQ > p && 10u * op > 9u * p;
+      dense = TB200_LZ4_DENSE_SEQ != 0u && p >= TB200_LZ4_DENSE_MIN && nseq * TB200_LZ4_DENSE_SEQ > p && TB200_LZ4_DENSE_OUT * op > 8u * p;
       // like lz4.c:1118, remember one position inside the match tail
       if (lane == 0 && p - 2 <= mflimit) table[(smem_read32(src, p - 2) * 2654435761u) >> (32 - HLOG)] = (uint16_t)(p - 2);
       __syncwarp();
