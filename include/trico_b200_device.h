@@ -74,9 +74,11 @@ TB200_API int tb200_fpc_encode_v0(tb200_ctx* ctx, int wordsize, const void* d_in
                         int e1, int e2, uint8_t* d_out, uint64_t out_stride, uint32_t* d_nbytes);
 TB200_API uint64_t tb200_fpc_v0_bound(int wordsize, uint32_t n);
 /* Decodes `nstreams` v0 streams found at d_base + offsets[c] (host array of offsets);
- * hash_info[c] = first byte of each stream (host knows it from the archive) selects table sizes.
- * Element j of stream c goes to d_out[j*stride + c]. */
-TB200_API int tb200_fpc_decode_v0(tb200_ctx* ctx, int wordsize, const uint8_t* d_base, const uint64_t* offsets,
+ * lengths[c] = bytes of the device buffer that are readable from the stream's first byte on (the
+ * kernel fetches the stream in 16-byte pieces and never reads beyond this; NULL: at least 4 KiB
+ * past the last byte of every stream are readable); hash_info[c] = first byte of each stream (host
+ * knows it from the archive) selects table sizes.  Element j of stream c goes to d_out[j*stride + c]. */
+TB200_API int tb200_fpc_decode_v0(tb200_ctx* ctx, int wordsize, const uint8_t* d_base, const uint64_t* offsets, const uint64_t* lengths,
                         const uint8_t* hash_info, int nstreams, uint32_t expect_n, void* d_out, uint32_t stride);
 
 /* ---- chunked byte-plane + LZ4: replaces trico_transpose_uint{16,32,64}_aos_to_soa +

@@ -15,7 +15,8 @@ WAVE = S * NL
 MINMATCH, LASTLITERALS, MFLIMIT = 4, 5, 12
 
 
-def parse_lanes(data: bytes, HLOG=10, OWNBITS=5, lazy=True, use_rep=True):
+def parse_lanes(data: bytes, HLOG=10, OWNBITS=5, lazy=True, use_rep=True, S=64, longest=False, merge=True):
+    WAVE = S * NL
     n = len(data)
     d = np.frombuffer(data, np.uint8)
     if n < MFLIMIT + 1:
@@ -70,19 +71,22 @@ def parse_lanes(data: bytes, HLOG=10, OWNBITS=5, lazy=True, use_rep=True):
             res = {}
             for l in probes:
                 q = pos[l]; h = hs[q]; ho = h >> (HLOG - OWNBITS)
-                c = -1
+                cands = []
                 if use_rep and wave_rep and q >= wave_rep and w32[q - wave_rep] == w32[q]:
-                    c = q - wave_rep
-                if c < 0:
-                    co = sub[l] + OWN[l][ho]
-                    if co < q and w32[co] == w32[q]: c = co
-                if c < 0:
-                    c1 = Tc[h]
-                    if c1 < q and w32[c1] == w32[q]: c = c1
-                if c < 0:
-                    c0 = To[h]
-                    if c0 < q and w32[c0] == w32[q]: c = c0
-                res[l] = c
+                    cands.append(q - wave_rep)
+                co = sub[l] + OWN[l][ho]
+                if co < q and w32[co] == w32[q]: cands.append(co)
+                c1 = Tc[h]
+                if c1 < q and w32[c1] == w32[q]: cands.append(c1)
+                c0 = To[h]
+                if c0 < q and w32[c0] == w32[q]: cands.append(c0)
+                if not cands:
+                    res[l] = -1
+                elif longest and len(cands) > 1:
+                    lim = min(end[l], matchlimit)
+                    res[l] = max(cands, key=lambda c: (mlen(q, c, lim), c))
+                else:
+                    res[l] = cands[0]
             for l in probes:                      # inserts after all look-ups of the step; the highest position of a bucket wins
                 q = pos[l]; h = hs[q]
                 OWN[l][h >> (HLOG - OWNBITS)] = q - sub[l]
@@ -123,7 +127,7 @@ def parse_lanes(data: bytes, HLOG=10, OWNBITS=5, lazy=True, use_rep=True):
             for i, (q, ml, off) in enumerate(lst[l]):
                 if held is not None:
                     hq, hml, hoff = held
-                    if i == 0 and q == sub[l] and hq + hml == q and hoff == off:
+                    if merge and i == 0 and q == sub[l] and hq + hml == q and hoff == off:
                         held = (hq, hml + ml, hoff)
                         continue
                     seqs.append((hq - emitted_to, hml, hoff)); emitted_to = hq + hml; held = None
@@ -181,20 +185,8 @@ if __name__ == "__main__":
 
     bun = np.load(os.path.join(ROOT, "tests", "golden", "bunny_full.npz"))
     pl = np.ascontiguousarray(bun["triangles"].reshape(-1).view(np.uint8).reshape(-1, 4)[:, 1])
-    for kw in (dict(), dict(HLOG=11), dict(use_rep=False), dict(lazy=False)):
-        run("bunny p1", pl, **kw)
-    v, tt = grid_mesh(500, 500, jitter=1.0, seed=1)
-    tp = tt.reshape(-1).view(np.uint8).reshape(-1, 4)
-    for p in range(4):
-        run(f"grid p{p}", np.ascontiguousarray(tp[:, p]))
-    run("grid p1", np.ascontiguousarray(tp[:, 1]), use_rep=False)
-    rng = np.random.default_rng(5)
-    py, pz = v[:, 1].astype(np.float64), v[:, 2].astype(np.float64)
-    g = np.clip(128 + 100 * np.sin(0.5 * py) + rng.integers(-4, 5, size=py.shape), 0, 255).astype(np.uint8)
-    run("col g", g, B=8192); run("col g", g)
-    side = 300
-    xs, ys = np.meshgrid(np.arange(side), np.arange(side))
-    u8 = (((xs >> 4) + (ys >> 4)) & 255).astype(np.uint8).reshape(-1)
-    run("u8", u8)
-    h16 = np.clip((pz + 5.5) * 5000, 0, 65535).astype(np.uint16)
-    run("u16 hi", np.ascontiguousarray(h16.view(np.uint8).reshape(-1, 2)[:, 1]), B=8192)
+    which = sys.argv[1] if len(sys.argv) > 1 else "sweep"
+    if which == "sweep":
+        for kw in (dict(S=64), dict(S=64, longest=True), dict(S=128, longest=True), dict(S=256, longest=True), dict(S=512, longest=True), dict(S=512, longest=True, HLOG=11), dict(S=512, longest=True, HLOG=12),
+                   dict(S=512, longest=True, HLOG=12, merge=False), dict(S=256, longest=True, HLOG=12)):
+            run("bunny p1", pl, **kw)

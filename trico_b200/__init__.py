@@ -56,7 +56,7 @@ def load() -> C.CDLL:
         "tb200_fpc_decode": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, _vp]),
         "tb200_fpc_encode_v0": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, _vp]),
         "tb200_fpc_v0_bound": (C.c_uint64, [C.c_int, C.c_uint32]),
-        "tb200_fpc_decode_v0": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_uint32, _vp, C.c_uint32]),
+        "tb200_fpc_decode_v0": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_uint32, _vp, C.c_uint32]),
         "tb200_lz4_encode": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp, _vp]),
         "tb200_lz4_decode": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_uint64, C.c_uint64, C.c_int, _vp]),
         "tb200_lz4_decode_v0": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint64, _vp]),

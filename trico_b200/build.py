@@ -20,7 +20,7 @@ LIB = os.environ.get("TRICO_B200_LIB") or os.path.join(LIBDIR, "libtrico_b200.so
 ROOT = os.path.dirname(HERE)
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("TB200_NVCC_EXTRA", "").split()
 CC_FLAGS = ["-O2", "-fPIC", "-std=c11", "-Wall", "-Wextra", "-Wno-unused-parameter", "-fvisibility=hidden",
             "-D_POSIX_C_SOURCE=200809L"]
 

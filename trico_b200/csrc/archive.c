@@ -776,7 +776,11 @@ static int read_stream(void* h, int type, void** out, int alloc_result)
       if (a->version == 1)
         ok = tb200_decode_stream(w->ctx, head, d_stream, end - start, d_dst);
       else if (codec == 1)
-        ok = tb200_fpc_decode_v0(w->ctx, ws, d_stream, sub_off, sub_info, nsub, (uint32_t)n, d_dst, (uint32_t)nc);
+        {
+        uint64_t sub_room[8];                /* bytes of the uploaded stream that follow each component's first byte */
+        for (int s = 0; s < nsub; ++s) sub_room[s] = (end - start) - sub_off[s];
+        ok = tb200_fpc_decode_v0(w->ctx, ws, d_stream, sub_off, sub_room, sub_info, nsub, (uint32_t)n, d_dst, (uint32_t)nc);
+        }
       else
         ok = tb200_lz4_decode_v0(w->ctx, nsub, d_stream, sub_off, sub_len, n, d_dst);
       if (!ok) set_dev_err();
@@ -891,6 +895,7 @@ static void decompress_any(uint32_t* n_out, void** out, const uint8_t* compresse
   int ok = 1;
   const uint8_t* d_stream = compressed;
   uint32_t n = 0;
+  uint64_t extent_bytes = 0;
   if (on_dev)
     {
     ok = tb200_memcpy_d2h(w->ctx, hdr, compressed, 5) && tb200_ctx_sync(w->ctx);
@@ -899,6 +904,7 @@ static void decompress_any(uint32_t* n_out, void** out, const uint8_t* compresse
     {
     memcpy(hdr, compressed, 5);
     const uint64_t extent = fpc_stream_extent(compressed, ws);
+    extent_bytes = extent;
     ok = ensure(&w->d_enc, &w->enc_cap, extent + 256, w) && tb200_memcpy_h2d(w->ctx, w->d_enc, compressed, extent);
     d_stream = w->d_enc;
     }
@@ -907,7 +913,7 @@ static void decompress_any(uint32_t* n_out, void** out, const uint8_t* compresse
   void* host = malloc(raw ? raw : 1);                 /* the reference allocates the result (:231, :822) */
   ok = ok && host && ensure(&w->d_raw, &w->raw_cap, raw + 64, w);
   const uint64_t zero = 0;
-  if (ok && n) ok = tb200_fpc_decode_v0(w->ctx, ws, d_stream, &zero, hdr, 1, n, w->d_raw, 1) &&
+  if (ok && n) ok = tb200_fpc_decode_v0(w->ctx, ws, d_stream, &zero, on_dev ? NULL : &extent_bytes, hdr, 1, n, w->d_raw, 1) &&
                    tb200_memcpy_d2h(w->ctx, host, w->d_raw, raw) && tb200_ctx_sync(w->ctx);
   if (ok) { *out = host; *n_out = n; }
   else { set_dev_err(); free(host); }

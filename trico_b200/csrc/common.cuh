@@ -1,7 +1,11 @@
 // common.cuh - device helpers shared by the trico_b200 kernels (sm_100a).
 #pragma once
 
+#ifdef TB200_HOST_EMU
+#include "warp_emu.hpp"            // tools/sim: the device source compiled for the CPU, one std::thread per lane
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace tb200 {
@@ -9,6 +13,10 @@ namespace tb200 {
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+#ifdef TB200_HOST_EMU
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << lane_id()) - 1u; }
+__device__ __forceinline__ unsigned lanemask_gt() { return lane_id() == 31u ? 0u : ~((2u << lane_id()) - 1u); }
+#else
 __device__ __forceinline__ unsigned lanemask_lt()
   {
   unsigned m; asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
@@ -17,6 +25,7 @@ __device__ __forceinline__ unsigned lanemask_gt()
   {
   unsigned m; asm volatile("mov.u32 %0, %%lanemask_gt;" : "=r"(m)); return m;
   }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Single-pass chained scan ("decoupled look-back") over tile aggregates.

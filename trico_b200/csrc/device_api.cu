@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "fpc.cuh"
 #include "lz4.cuh"
+#include "lz4_lanes.cuh"
 #include "planes.cuh"
 
 #include <stdio.h>
@@ -414,7 +415,7 @@ extern "C" int tb200_fpc_encode_v0(tb200_ctx* c, int wordsize, const void* d_in,
   return 1;
   }
 
-extern "C" int tb200_fpc_decode_v0(tb200_ctx* c, int wordsize, const uint8_t* d_base, const uint64_t* offsets,
+extern "C" int tb200_fpc_decode_v0(tb200_ctx* c, int wordsize, const uint8_t* d_base, const uint64_t* offsets, const uint64_t* lengths,
                                    const uint8_t* hash_info, int nstreams, uint32_t expect_n, void* d_out, uint32_t stride)
   {
   CK(cudaSetDevice(c->device));
@@ -426,26 +427,27 @@ extern "C" int tb200_fpc_decode_v0(tb200_ctx* c, int wordsize, const uint8_t* d_
     const size_t t = ((size_t)1 << ((hash_info[s] >> 4) << 1)) + ((size_t)1 << ((hash_info[s] & 15) << 1));
     if (t > tw) tw = t;
     }
-  // pointer table + counts live at the start of the big scratch; tables (if global) follow
+  // pointer table, stream lengths and counts live at the start of the big scratch; tables (if global) follow
   const size_t head = 256;
-  const bool global_tables = tw * wordsize > 64 * 1024;
+  const bool global_tables = tw * wordsize > 48 * 1024;
   uint8_t* g = nullptr;
   if (!big_prepare(c, head + (global_tables ? tw * wordsize * nstreams : 0), &g)) return 0;
-  const uint8_t* ptrs[8];
-  for (int s = 0; s < nstreams; ++s) ptrs[s] = d_base + offsets[s];
-  CK(cudaMemcpyAsync(g, ptrs, sizeof(void*) * nstreams, cudaMemcpyHostToDevice, c->stream));
+  struct { const uint8_t* ptrs[8]; uint64_t len[8]; } hdr;
+  for (int s = 0; s < 8; ++s) { hdr.ptrs[s] = s < nstreams ? d_base + offsets[s] : nullptr; hdr.len[s] = (s < nstreams && lengths) ? lengths[s] : 0; }
+  CK(cudaMemcpyAsync(g, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, c->stream));
   FpcLegacyDecodeArgs a;
   a.streams = reinterpret_cast<const uint8_t* const*>(g);
+  a.extents = lengths ? reinterpret_cast<const uint64_t*>(g + 64) : nullptr;
   a.nstreams = nstreams; a.out = d_out; a.stride = stride;
-  a.counts = reinterpret_cast<uint32_t*>(g + 128);
+  a.counts = reinterpret_cast<uint32_t*>(g + 192);
   a.expect = expect_n;
   a.gtables = nullptr; a.gtable_words = tw;
-  size_t smem = tw * wordsize;
+  size_t smem = FPC_LEGACY_RING + tw * wordsize;
   if (global_tables)
     {
     a.gtables = g + head;
     CK(cudaMemsetAsync(g + head, 0, tw * wordsize * nstreams, c->stream));
-    smem = 0;
+    smem = FPC_LEGACY_RING;
     }
   if (wordsize == 4)
     {
@@ -459,7 +461,7 @@ extern "C" int tb200_fpc_decode_v0(tb200_ctx* c, int wordsize, const uint8_t* d_
     }
   c->launches++;
   CK(cudaGetLastError());
-  // ptrs[] is a stack array consumed by an async copy from pageable memory: CUDA stages pageable
+  // hdr is a stack object consumed by an async copy from pageable memory: CUDA stages pageable
   // sources before returning, so no synchronisation is needed here.
   return 1;
   }

@@ -1165,8 +1165,18 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
 
 // ---------------------------------------------------------------------------------------------
 // K4L: legacy (reference v0) stream decoder.  The whole stream is ONE serial chain
-// (fpc.c:246-327), so a stream is decoded by a single lane; block b decodes stream b.
-// Tables: shared memory when they fit, else global scratch (zeroed by the host).
+// (fpc.c:246-327): value j needs the decoded value j-1 for both table look-ups, so a stream is
+// one dependency chain of ~50 cycles per value whatever the hardware.  What the warp can do is
+// keep everything else off that chain (block b decodes stream b):
+//   * the compressed bytes travel through a 4 KiB ring in shared memory, filled 2 KiB ahead with
+//     16-byte cp.async copies (the old kernel read every residual byte from global memory);
+//   * per step of 32 values all lanes walk the code words of the step (4 groups of 8 floats,
+//     16 groups of 2 doubles), lane j then gathers the residual of value j;
+//   * lane 0 alone runs the predictor over the 32 values, taking each residual from its lane by
+//     a shuffle (issued ahead, off the chain) and handing each value back the same way;
+//   * the 32 values leave as one strided warp store.
+// Tables: shared memory when they fit ((4,10) floats: 4 KiB), else global scratch zeroed by the
+// host ((20,20) doubles: 16 MiB per stream - every look-up is then an L2 round trip).
 // ---------------------------------------------------------------------------------------------
 struct FpcLegacyDecodeArgs
   {
@@ -1178,7 +1188,10 @@ struct FpcLegacyDecodeArgs
   uint64_t gtable_words;           // per stream
   uint32_t* counts;                // [nstreams] decoded value counts (from the stream headers)
   uint32_t expect;                 // values the caller has room for per stream
+  const uint64_t* extents;         // [nstreams] bytes of the buffer readable from each stream's first byte (0: unknown)
   };
+
+constexpr uint32_t FPC_LEGACY_RING = 4096;
 
 template <typename W>
 __global__ void __launch_bounds__(32)
@@ -1186,39 +1199,92 @@ fpc_decode_legacy_kernel(const FpcLegacyDecodeArgs a)
   {
   using TR = FpcTraits<W>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const unsigned c = blockIdx.x;
+  uint8_t* ring = smem_raw;                                        // FPC_LEGACY_RING bytes
+  const unsigned c = blockIdx.x, lane = lane_id();
   const uint8_t* p = a.streams[c];
   const int e1 = (p[0] >> 4) << 1, e2 = (p[0] & 15) << 1;          // fpc.c:214-217
   const uint32_t n = ((uint32_t)p[1] << 24) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 8) | p[4];
   const size_t nt1 = (size_t)1 << e1, nt2 = (size_t)1 << e2;
   W* T1; W* T2;
-  const bool in_smem = a.gtables == nullptr;
-  if (in_smem) { T1 = reinterpret_cast<W*>(smem_raw); for (size_t i = threadIdx.x; i < nt1 + nt2; i += 32) T1[i] = 0; }
+  if (a.gtables == nullptr) { T1 = reinterpret_cast<W*>(smem_raw + FPC_LEGACY_RING); for (size_t i = lane; i < nt1 + nt2; i += 32) T1[i] = 0; }
   else T1 = reinterpret_cast<W*>(a.gtables) + (size_t)c * a.gtable_words;
   T2 = T1 + nt1;
-  __syncwarp();
-  if (threadIdx.x != 0) return;
-  a.counts[c] = n;
+  if (lane == 0) a.counts[c] = n;
   const uint32_t todo = n < a.expect ? n : a.expect;
-  p += 5;
+  // the ring holds stream bytes [ring_lo, ring_hi) of the 16-byte aligned view of the stream
+  const uint8_t* base = p - (reinterpret_cast<uintptr_t>(p) & 15u);
+  const uint64_t readable = a.extents && a.extents[c] ? a.extents[c] + (uint64_t)(p - base) : ~0ull;   // from base
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  uint64_t bp = (uint64_t)(p - base) + 5;                          // next unread byte, relative to base
+  uint64_t hi = 0;                                                 // bytes [0, hi) have been requested
+  auto request = [&](uint64_t upto)
+    { // cp.async of whole 16-byte vectors up to `upto` (a multiple of 2048); bytes beyond the buffer are zero filled
+    for (uint64_t o = hi + 16ull * lane; o < upto; o += 512)
+      {
+      const uint32_t ssz = o + 16 <= readable ? 16u : (o < readable ? (uint32_t)(readable - o) : 0u);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(ring_s + (uint32_t)(o & (FPC_LEGACY_RING - 1))), "l"(base + (ssz ? o : 0)), "r"(ssz) : "memory");
+      }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    hi = upto;
+    };
+  request(FPC_LEGACY_RING);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  auto rb = [&](uint64_t o) -> uint32_t { return ring[o & (FPC_LEGACY_RING - 1)]; };
+
   FpcLaneState<W> st; st.pred1 = 0; st.pred2 = 0; st.last = 0; st.c1 = 0; st.c2 = 0;
   const uint32_t m2 = (uint32_t)nt2 - 1;
   W* out = reinterpret_cast<W*>(a.out) + c;
-  for (uint32_t i = 0; i < todo; i += TR::GROUP)
+  constexpr int GPS = 32 / TR::GROUP;                              // groups per step
+  const uint32_t gl = lane % TR::GROUP, gi = lane / TR::GROUP;
+  for (uint32_t i0 = 0; i0 < todo; i0 += 32)
     {
-    uint32_t bc = 0;
-    for (int b = 0; b < TR::HDR; ++b) bc = (bc << 8) | *p++;
-#pragma unroll
-    for (int jj = 0; jj < TR::GROUP; ++jj)
+    // keep two kilobytes ahead: the half of the ring behind the read position is free
+    const uint64_t target = ((bp >> 11) + 2) << 11;
+    if (target > hi) request(target);
+    if (bp + 320 > hi - 2048) asm volatile("cp.async.wait_group 0;" ::: "memory");      // the step reaches into the newest half
+    else asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    // code words of the step: every lane walks them, lane j keeps the place of residual j
+    uint64_t gp = bp, my_at = 0;
+    uint32_t my_nb = 0;
+    bool my_use2 = false;
+#pragma unroll 1
+    for (int g = 0; g < GPS; ++g)
       {
-      const uint32_t code = (bc >> (TR::CBITS * jj)) & ((1u << TR::CBITS) - 1u);
-      const bool use2 = code > (uint32_t)TR::BASE2;
-      const uint32_t nb = use2 ? code - TR::BASE2 : code;
-      W x = 0;
-      for (uint32_t b = 0; b < nb; ++b) x = (x << 8) | *p++;
-      if (i + jj < todo)
-        out[(size_t)(i + jj) * a.stride] = fpc_decode_value<W, 1>(st, x, use2, T1, T2, e1, e2, m2);
+      uint32_t bc = 0;
+#pragma unroll
+      for (int b = 0; b < TR::HDR; ++b) bc = (bc << 8) | rb(gp + b);
+      uint32_t sum = 0;
+#pragma unroll
+      for (int jj = 0; jj < TR::GROUP; ++jj)
+        {
+        const uint32_t code = (bc >> (TR::CBITS * jj)) & ((1u << TR::CBITS) - 1u);
+        const uint32_t nb = code > (uint32_t)TR::BASE2 ? code - TR::BASE2 : code;
+        if ((uint32_t)g == gi && (uint32_t)jj == gl) { my_at = gp + TR::HDR + sum; my_nb = nb; my_use2 = code > (uint32_t)TR::BASE2; }
+        sum += nb;
+        }
+      gp += TR::HDR + sum;
       }
+    // residual of value i0 + lane, big-endian
+    W x = 0;
+    for (uint32_t b = 0; b < my_nb; ++b) x = (W)(x << 8) | (W)rb(my_at + b);
+    __syncwarp();
+    // the chain: lane 0 only
+    W mine = 0;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j)
+      {
+      const W xj = __shfl_sync(FULL, x, j);
+      const bool u2 = __shfl_sync(FULL, (int)my_use2, j) != 0;
+      W v = 0;
+      if (lane == 0 && i0 + (uint32_t)j < todo) v = fpc_decode_value<W, 1>(st, xj, u2, T1, T2, e1, e2, m2);
+      v = __shfl_sync(FULL, v, 0);
+      if ((int)lane == j) mine = v;
+      }
+    if (i0 + lane < todo) out[(size_t)(i0 + lane) * a.stride] = mine;
+    // bytes of the values that exist (the pad slots of a last, incomplete group do not matter any more)
+    bp = gp;
     }
   }
 

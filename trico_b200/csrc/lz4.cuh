@@ -165,7 +165,7 @@ __device__ __forceinline__ uint32_t lz4_emit_run(DstPtr dst, uint32_t n, uint32_
 #define TB200_LZ4_DENSE_SEQ 24u        // bytes per sequence below which a block counts as dense (0: never)
 #endif
 #ifndef TB200_LZ4_DENSE_OUT
-#define TB200_LZ4_DENSE_OUT 10u        // ... while the output stays above 8 / TB200_LZ4_DENSE_OUT of the input
+#define TB200_LZ4_DENSE_OUT 9u         // ... while the output stays above TB200_LZ4_DENSE_OUT tenths of the input
 #endif
 constexpr uint32_t LZ4_SRC_PAD = 576;    // zeroed bytes the compressor may read past the block end (512-byte match extension steps)
 constexpr uint32_t LZ4_ENC_STAGE = 128;  // per-warp staging bytes for the sequences of one window (lz4_compress_warp)
@@ -192,8 +192,12 @@ constexpr uint32_t LZ4_WIN_CAP = 36;     // match lengths are measured up to thi
 // Table inserts follow the reference: literal positions and match starts, not match interiors
 // (lz4.c:1118 adds one position near the end of a match) - the interior positions of a run would
 // replace the candidate at the run's start, which is the one that extends across the run.
+// `handover`: a block that averages less than LZ4_HANDOVER_SEQ bytes per sequence once
+// LZ4_HANDOVER_MIN bytes have been parsed is not finished: the function returns 0xffffffff and the
+// caller passes the block to the lane-parallel parser (lz4_lanes.cuh).
+constexpr uint32_t LZ4_HANDOVER_MIN = 1024, LZ4_HANDOVER_SEQ = 16;
 template <int HLOG, typename DstPtr>
-__device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* table, uint8_t* stage, unsigned long long* dbg = nullptr)
+__device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* table, uint8_t* stage, bool handover = false, unsigned long long* dbg = nullptr)
   {
 #define TB200_EPH(i) do { if (dbg) { const long long t__ = clock64(); acc_ph[i] += (uint32_t)(t__ - t_ph); t_ph = t__; } } while (0)
   long long t_ph = dbg ? clock64() : 0;
@@ -211,7 +215,7 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
     // Dense mode: data that yields a match every few bytes WITHOUT getting smaller for it (noisy
     // planes: colours, quantised heights - four equal bytes turn up by chance all the time) pays
     // for every sequence twice, here and in the decoder.  Once the sequences of the block average
-    // less than TB200_LZ4_DENSE_SEQ bytes and the output so far is above 80 % of the input, a
+    // less than TB200_LZ4_DENSE_SEQ bytes and the output so far is above 90 % of the input, a
     // match has to be 8 bytes long to be taken.  (Blocks that do compress with short matches -
     // index planes of real meshes - never get here.)
     bool dense = false;
@@ -449,7 +453,8 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
           anchor = p + end_rel;
           p = pnew;
           nseq += (uint32_t)__popc(kept);
-          dense = TB200_LZ4_DENSE_SEQ != 0u && anchor >= TB200_LZ4_DENSE_MIN && nseq * TB200_LZ4_DENSE_SEQ > anchor && TB200_LZ4_DENSE_OUT * op > 8u * anchor;
+          if (handover && anchor >= LZ4_HANDOVER_MIN && nseq * LZ4_HANDOVER_SEQ > anchor) return 0xffffffffu;
+          dense = TB200_LZ4_DENSE_SEQ != 0u && anchor >= (handover ? LZ4_HANDOVER_MIN : TB200_LZ4_DENSE_MIN) && nseq * TB200_LZ4_DENSE_SEQ > anchor && 10u * op > TB200_LZ4_DENSE_OUT * anchor;
           TB200_EPH(1);
           continue;
           }
@@ -507,7 +512,8 @@ long_match:
       op = lz4_emit(dst, op, src, anchor, mq - anchor, mq - mc, len);
       p = anchor = mq + len;
       ++nseq;
-      dense = TB200_LZ4_DENSE_SEQ != 0u && p >= TB200_LZ4_DENSE_MIN && nseq * TB200_LZ4_DENSE_SEQ > p && TB200_LZ4_DENSE_OUT * op > 8u * p;
+      if (handover && p >= LZ4_HANDOVER_MIN && nseq * LZ4_HANDOVER_SEQ > p) return 0xffffffffu;
+      dense = TB200_LZ4_DENSE_SEQ != 0u && p >= (handover ? LZ4_HANDOVER_MIN : TB200_LZ4_DENSE_MIN) && nseq * TB200_LZ4_DENSE_SEQ > p && 10u * op > TB200_LZ4_DENSE_OUT * p;
       // like lz4.c:1118, remember one position inside the match tail
       if (lane == 0 && p - 2 <= mflimit) table[(smem_read32(src, p - 2) * 2654435761u) >> (32 - HLOG)] = (uint16_t)(p - 2);
       __syncwarp();
@@ -688,6 +694,8 @@ struct Lz4EncodeArgs
   uint32_t slot;           // bytes per scratch slot (>= lz4_block_bound(B), multiple of 16)
   uint64_t* desc;          // look-back descriptors of the assemble kernel, zeroed
   uint32_t* ticket;        // chunk ticket, zeroed
+  uint32_t* dense_list;    // chunk ids handed over to lz4_encode_dense_kernel (nullptr: never hand over)
+  uint32_t* dense_count;   // zeroed
   unsigned long long* dbg; // phase-cycle counters by plane (experiments; nullptr in production)
   };
 
@@ -844,7 +852,12 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
         if (a.dbg && lane == 0) { const long long t2 = clock64(); atomicAdd(a.dbg + (p & 7), (unsigned long long)(t2 - t_ph)); t_ph = t2; }
 
         // 2. compress into this chunk's slot
-        nbytes = lz4_compress_warp<HLOG>(buf, cnt, a.scratch + g * a.slot, table, stage, a.dbg ? a.dbg + 16 + 8 * (p & 7) : nullptr);
+        nbytes = lz4_compress_warp<HLOG>(buf, cnt, a.scratch + g * a.slot, table, stage, a.dense_list != nullptr, a.dbg ? a.dbg + 16 + 8 * (p & 7) : nullptr);
+        if (nbytes == 0xffffffffu)
+          { // many short sequences: the lane-parallel parser of the second pass takes this block
+          if (lane == 0) a.dense_list[atomicAdd(a.dense_count, 1u)] = (uint32_t)g;
+          nbytes = 0;
+          }
         }
       if (a.dbg && lane == 0) { const long long t2 = clock64(); atomicAdd(a.dbg + 8 + (p & 7), (unsigned long long)(t2 - t_ph)); }
       if (lane == 0)
@@ -864,6 +877,7 @@ lz4_encode_kernel(const Lz4EncodeArgs a)
 constexpr int LZ4_ASM_THREADS = 256;
 constexpr int LZ4_ASM_TILE = 128;           // 64 measured the same, 256 slower
 
+#ifndef TB200_HOST_EMU
 __global__ void __launch_bounds__(LZ4_ASM_THREADS)
 lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
   {
@@ -970,6 +984,8 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
     for (uint32_t i = lane; i < nbytes; i += 32) dst[i] = __ldcs(src + i);
     }
   }
+
+#endif // TB200_HOST_EMU
 
 // ---------------------------------------------------------------------------------------------
 // In-place block decoder on shared memory (K6).  The compressed block sits at the END of the
@@ -1137,7 +1153,9 @@ __device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint3
 // Returns the number of sequences done (0: the next one is not of this kind), -1 on a malformed one.
 constexpr uint32_t LZ4_BATCH_MAXMATCH = 64;
 constexpr uint32_t LZ4_BATCH_MAXLIT = 32;
-__device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint32_t iend, uint32_t& op, uint32_t cap)
+// ib: compressed bytes, ob: output (the same buffer for the in-place decoder); `floor`: index of the
+// first real output byte in ob (offsets must not reach below it).
+__device__ __forceinline__ int lz4_decode_batch(const uint8_t* ib, uint8_t* ob, uint32_t& ip, uint32_t iend, uint32_t& op, uint32_t cap, uint32_t floor = 0)
   {
   const unsigned lane = lane_id();
   uint32_t sp = ip, o = op;
@@ -1147,13 +1165,13 @@ __device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint
   for (int k = 0; k < 32; ++k)
     {
     if (sp >= iend) break;
-    const uint32_t t = buf[sp];
+    const uint32_t t = ib[sp];
     uint32_t lit = t >> 4;
     const uint32_t mlc = t & 15u;
     uint32_t adv = 3u;
     if (lit == 15u)
       {
-      const uint32_t x = buf[sp + 1u];
+      const uint32_t x = ib[sp + 1u];
       if (x > LZ4_BATCH_MAXLIT - 15u) break;                // long literal run
       lit += x; ++adv;
       }
@@ -1162,10 +1180,11 @@ __device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint
     uint32_t ml = LZ4_MINMATCH + mlc;
     if (mlc == 15u)
       {
-      const uint32_t x = buf[sp + adv];
+      const uint32_t x = ib[sp + adv];
       if (x > LZ4_BATCH_MAXMATCH - 19u) break;              // long match (or a longer continuation)
       ml += x; ++adv;
       }
+    if (o + lit + ml > cap) break;                            // does not fit (a malformed block, or the end of a segment: the caller decides)
     if ((int)lane == k) { my_sp = sp; my_op = o; my_lit = lit; my_ml = ml; }
     sp += adv; o += lit + ml; ++nseq;
     }
@@ -1179,14 +1198,14 @@ __device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       {
-      if (my_lit > 8u * u) lw[u] = (uint64_t)smem_read32(buf, l0 + 8u * u);
-      if (my_lit > 8u * u + 4u) lw[u] |= (uint64_t)smem_read32(buf, l0 + 8u * u + 4u) << 32;
+      if (my_lit > 8u * u) lw[u] = (uint64_t)smem_read32(ib, l0 + 8u * u);
+      if (my_lit > 8u * u + 4u) lw[u] |= (uint64_t)smem_read32(ib, l0 + 8u * u + 4u) << 32;
       }
     const uint32_t e = l0 + my_lit;
-    off = (uint32_t)buf[e] | ((uint32_t)buf[e + 1u] << 8);
+    off = (uint32_t)ib[e] | ((uint32_t)ib[e + 1u] << 8);
     }
   const uint32_t dst = my_op + my_lit;
-  const bool fine = !act || (off != 0u && off <= dst && dst + my_ml <= cap);
+  const bool fine = !act || (off != 0u && off <= dst - floor && dst + my_ml <= cap);
   if (!__all_sync(FULL, fine)) return -1;
   __syncwarp();
   if (act)
@@ -1194,7 +1213,7 @@ __device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       for (uint32_t j = 8u * u; j < my_lit && j < 8u * u + 8u; ++j)
-        buf[my_op + j] = (uint8_t)(lw[u] >> (8u * (j - 8u * u)));
+        ob[my_op + j] = (uint8_t)(lw[u] >> (8u * (j - 8u * u)));
     }
   __syncwarp();
   // the matches of earlier sequences this lane's source overlaps: [s, e) = the part of the source
@@ -1213,8 +1232,8 @@ __device__ __forceinline__ int lz4_decode_batch(uint8_t* buf, uint32_t& ip, uint
     if (und == 0) break;
     if (open && (und & waits) == 0)
       {
-      const uint8_t* ms = buf + dst - off;
-      uint8_t* md = buf + dst;
+      const uint8_t* ms = ob + dst - off;
+      uint8_t* md = ob + dst;
       if (off >= 4u)
         { // four bytes per step: the loads of a step lie before its first store
         for (uint32_t j = 0; j < my_ml; j += 4u)
@@ -1270,7 +1289,7 @@ __device__ __forceinline__ uint32_t lz4_decode_inplace(uint8_t* buf, uint32_t ip
     {
     if (batching)
       {
-      const int nb = lz4_decode_batch(buf, ip, iend, op, cap);
+      const int nb = lz4_decode_batch(buf, buf, ip, iend, op, cap);
       if (nb < 0) return 0xffffffffu;
       if (nb < 4) batching = false;
       if (nb > 0) { __syncwarp(); b = buf[ip + lane]; continue; }
@@ -1663,25 +1682,201 @@ lz4_decode_kernel(const Lz4DecodeArgs a)
   }
 
 // ---------------------------------------------------------------------------------------------
-// K6L: reference-format planes - ONE LZ4 block per whole plane (trico.c:346, :1101).  One warp per
-// plane decodes serially into a global plane buffer; the merge is a second kernel (planes.cuh).
+// K6L: reference-format planes - ONE LZ4 block per whole plane (trico.c:346, :1101), up to 2 GB.
+// A block is one serial chain of sequences, so a plane is decoded by one warp (block p = plane p);
+// what the warp can do is keep the chain in shared memory:
+//   * the compressed bytes pass through an 8 KiB window (16-byte cp.async fills);
+//   * the output is produced in a flat buffer of 64 KiB of history + a 16 KiB segment: every
+//     match source (offsets reach 65535 bytes back) is a shared-memory read, all copies are the
+//     warp-wide ones of the chunked decoder (512 bytes per step, periodic fill for short offsets),
+//     runs of short sequences go through the batch decoder (lz4_decode_batch);
+//   * a full segment leaves as coalesced 16-byte stores and the history moves down by a segment.
+// Sequences are cut at segment / window boundaries and continued after the flush / refill.
+// The planes are merged by a second kernel (planes.cuh).
 // ---------------------------------------------------------------------------------------------
 struct Lz4LegacyDecodeArgs
   {
   const uint8_t* src[8];
   uint32_t src_len[8];
-  uint8_t* planes;         // nplanes buffers of plane_stride bytes
+  uint8_t* planes;         // nplanes buffers of plane_stride bytes (16-byte aligned)
   uint64_t plane_stride;
   uint32_t raw_len;
   uint32_t* status;
   };
 
+constexpr uint32_t LZ4_LEG_HIST = 65536, LZ4_LEG_SEG = 16384, LZ4_LEG_IN = 8192;
+__host__ __device__ constexpr size_t lz4_legacy_smem() { return (size_t)LZ4_LEG_HIST + LZ4_LEG_SEG + 64 + LZ4_LEG_IN + 64; }
+
+// warp copy between two shared-memory buffers, any alignment, non-overlapping
+__device__ __forceinline__ void lz4_smem_copy(uint8_t* dst, const uint8_t* src, uint32_t n)
+  {
+  const unsigned lane = lane_id();
+  if (n <= 64u)
+    {
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    return;
+    }
+  const uint32_t head = (4u - ((uint32_t)__cvta_generic_to_shared(dst) & 3u)) & 3u;
+  if (lane < head) dst[lane] = src[lane];
+  const uint32_t nw = (n - head) >> 2;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  const uint8_t* sb = src + head;
+  const uint32_t sal = (uint32_t)__cvta_generic_to_shared(sb) & 3u;
+  const uint8_t* sbase = sb - sal;                         // 4-byte aligned
+  for (uint32_t i = lane; i < nw; i += 32) dw[i] = smem_read32(sbase, sal + 4u * i);
+  const uint32_t done = head + (nw << 2);
+  if (done + lane < n) dst[done + lane] = src[done + lane];
+  }
+
+#ifndef TB200_HOST_EMU
 __global__ void __launch_bounds__(32)
 lz4_decode_legacy_kernel(const Lz4LegacyDecodeArgs a)
   {
-  const unsigned p = blockIdx.x;
-  const uint32_t got = lz4_decompress_warp<true>(a.src[p], a.src_len[p], a.planes + (size_t)p * a.plane_stride, a.raw_len);
-  if (got != a.raw_len && lane_id() == 0) *a.status = 1;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* ob = smem_raw;                                            // [HIST | SEG | 64 spare]
+  uint8_t* ib = smem_raw + LZ4_LEG_HIST + LZ4_LEG_SEG + 64;          // [IN | 64 spare]
+  const unsigned lane = lane_id();
+  const unsigned pl = blockIdx.x;
+  const uint8_t* src = a.src[pl];
+  const uint32_t src_len = a.src_len[pl];
+  uint8_t* gout = a.planes + (size_t)pl * a.plane_stride;
+  const uint32_t raw_len = a.raw_len;
+  constexpr uint32_t CAP = LZ4_LEG_HIST + LZ4_LEG_SEG;
+
+  uint32_t consumed = 0;          // compressed bytes before ib[0]
+  uint32_t in_len = 0;            // valid bytes in ib
+  uint32_t ip = 0;                // next unread byte in ib
+  uint32_t seg_base = 0;          // output position of ob[HIST]
+  uint32_t op = LZ4_LEG_HIST;     // next output byte in ob
+  bool bad = false;
+
+  // moves the unread input to the front of the window and fills the rest from global memory
+  auto refill = [&]()
+    {
+    const uint32_t keep = in_len - ip;
+    if (ip != 0u)
+      {
+      for (uint32_t i0 = 0; i0 < keep; i0 += 32)
+        {
+        uint32_t t = 0;
+        if (i0 + lane < keep) t = ib[ip + i0 + lane];
+        __syncwarp();
+        if (i0 + lane < keep) ib[i0 + lane] = (uint8_t)t;
+        __syncwarp();
+        }
+      consumed += ip; ip = 0; in_len = keep;
+      }
+    const uint32_t left = src_len - (consumed + in_len);
+    const uint32_t take = min(left, LZ4_LEG_IN - in_len);
+    const uint8_t* g = src + consumed + in_len;
+    for (uint32_t i = lane; i < take; i += 32) ib[in_len + i] = __ldg(g + i);
+    in_len += take;
+    for (uint32_t i = lane; i < 64u; i += 32) ib[in_len + i] = 0;     // readable slack behind the window
+    __syncwarp();
+    };
+  // the segment is full (or the block is finished): write it out, move the history down
+  auto flush = [&](bool last)
+    {
+    uint32_t nout = op - LZ4_LEG_HIST;
+    if (seg_base + nout > raw_len) { bad = true; nout = raw_len - seg_base; }     // never write past the plane
+    const uint32_t nv = (reinterpret_cast<uintptr_t>(gout) & 15u) == 0 ? nout >> 4 : 0u;
+    uint4* gv = reinterpret_cast<uint4*>(gout + seg_base);
+    const uint4* sv = reinterpret_cast<const uint4*>(ob + LZ4_LEG_HIST);
+    for (uint32_t i = lane; i < nv; i += 32) gv[i] = sv[i];
+    for (uint32_t i = (nv << 4) + lane; i < nout; i += 32) gout[seg_base + i] = ob[LZ4_LEG_HIST + i];
+    __syncwarp();
+    if (!last)
+      { // history: ob[SEG .. SEG + HIST) -> ob[0 .. HIST); every batch is read completely before it is written
+      constexpr int UN = 4;
+      uint4* v = reinterpret_cast<uint4*>(ob);
+      for (uint32_t i0 = 0; i0 < LZ4_LEG_HIST / 16u; i0 += 32 * UN)
+        {
+        uint4 t[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) t[u] = v[LZ4_LEG_SEG / 16u + i0 + lane + 32 * u];
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < UN; ++u) v[i0 + lane + 32 * u] = t[u];
+        __syncwarp();
+        }
+      seg_base += nout; op = LZ4_LEG_HIST;
+      }
+    };
+  // reads a length continuation at ip (lz4.c:1629-1649), refilling the window as often as it takes
+  auto read_ext = [&]() -> uint32_t
+    {
+    uint32_t add = 0;
+    for (;;)
+      {
+      if (in_len - ip < 64u && consumed + in_len < src_len) refill();
+      const uint32_t avail = in_len - ip;
+      if (avail == 0u) { bad = true; return add; }
+      const uint32_t b = lane < avail ? ib[ip + lane] : 0u;
+      const unsigned m = __ballot_sync(FULL, b != 255u);
+      if (m == 0u) { add += 255u * 32u; ip += 32; continue; }         // (avail >= 32 here: a shorter window ends with a zero from the slack)
+      const int e = __ffs((int)m) - 1;
+      add += 255u * (uint32_t)e + __shfl_sync(FULL, b, e);
+      ip += (uint32_t)e + 1u;
+      return add;
+      }
+    };
+
+  if (src_len == 0u) bad = true;
+  else refill();
+  bool batching = false;
+  while (!bad)
+    {
+    if (in_len - ip < 1024u && consumed + in_len < src_len) refill();
+    if (consumed + ip >= src_len) { bad = true; break; }              // a block ends with a literal-only sequence, never here
+    const uint32_t floor = LZ4_LEG_HIST - min(seg_base, LZ4_LEG_HIST);
+    if (batching)
+      {
+      const int nb = lz4_decode_batch(ib, ob, ip, in_len, op, CAP, floor);
+      if (nb < 0) { bad = true; break; }
+      if (nb < 4) batching = false;
+      if (nb > 0) { __syncwarp(); if (op == CAP) flush(false); if (seg_base + (op - LZ4_LEG_HIST) > raw_len) bad = true; continue; }
+      }
+    const uint32_t token = ib[ip++];
+    uint32_t lit = token >> 4, ml = token & 15u;
+    if (lit == 15u) { lit += read_ext(); if (bad) break; }
+    // literals, in pieces: what the window holds, what the segment takes
+    uint32_t rem = lit;
+    while (rem != 0u && !bad)
+      {
+      if (ip == in_len) { if (consumed + in_len >= src_len) { bad = true; break; } refill(); }
+      if (op == CAP) flush(false);
+      const uint32_t piece = min(rem, min(in_len - ip, CAP - op));
+      if (seg_base + (op - LZ4_LEG_HIST) + piece > raw_len) { bad = true; break; }
+      lz4_smem_copy(ob + op, ib + ip, piece);
+      __syncwarp();
+      ip += piece; op += piece; rem -= piece;
+      }
+    if (bad) break;
+    if (consumed + ip >= src_len) break;                               // the last sequence has no match part
+    if (in_len - ip < 2u) refill();
+    if (in_len - ip < 2u) { bad = true; break; }
+    const uint32_t offset = (uint32_t)ib[ip] | ((uint32_t)ib[ip + 1] << 8);
+    ip += 2;
+    if (ml == 15u) { ml += read_ext(); if (bad) break; }
+    const uint32_t mlen = ml + LZ4_MINMATCH;
+    const uint32_t outpos = seg_base + (op - LZ4_LEG_HIST);
+    if (offset == 0u || offset > outpos || outpos + mlen > raw_len || outpos + mlen < outpos) { bad = true; break; }
+    rem = mlen;
+    while (rem != 0u)
+      {
+      if (op == CAP) flush(false);
+      const uint32_t piece = min(rem, CAP - op);
+      lz4_match_warp(ob, op, offset, piece);
+      __syncwarp();
+      op += piece; rem -= piece;
+      }
+    batching = lit <= LZ4_BATCH_MAXLIT && mlen <= 32u;
+    }
+  const uint32_t produced = seg_base + (op - LZ4_LEG_HIST);
+  if (!bad) flush(true);
+  if ((bad || produced != raw_len) && lane == 0) *a.status = 1;
   }
+
+#endif // TB200_HOST_EMU
 
 } // namespace tb200
