@@ -107,6 +107,23 @@ TB200_API int tb200_encode_stream(tb200_ctx* ctx, int type, const void* d_data, 
  * bytes (starting at the type byte) are on the device at d_stream. */
 TB200_API int tb200_decode_stream(tb200_ctx* ctx, const uint8_t* header, const uint8_t* d_stream, uint64_t stream_bytes, void* d_out);
 
+/* ---- batches of streams (many small meshes: BASELINE C5) ----
+ * The streams of a batch run concurrently on several CUDA streams of the context and nothing is
+ * synchronised or read back per stream.  tb200_encode_streams: stream i (types[i], d_data[i],
+ * counts[i], default chunking) is encoded into its slot of d_arena (>= tb200_batch_arena_bytes),
+ * then the streams are packed back to back into d_packed, in order: the bytes tb200_encode_stream
+ * produces one by one.  d_sizes: n device u64 (stream sizes); d_prefix: 2n + 2 device u64 - entries
+ * [0, n] receive the offsets of the streams in d_packed and the total, the rest is scratch.
+ * tb200_decode_streams: stream i = sizes[i] bytes at d_packed + offsets[i] (host arrays) with its
+ * 15 header bytes at headers + 15 i (host); malformed LZ4 blocks set *d_status (device word the
+ * caller zeroed) - checked by the caller after its own synchronisation. */
+TB200_API uint64_t tb200_batch_arena_bytes(int n, const int* types, const uint32_t* counts);
+TB200_API int tb200_encode_streams(tb200_ctx* ctx, int n, const int* types, const void* const* d_data, const uint32_t* counts,
+                        uint8_t* d_arena, uint64_t arena_cap, uint8_t* d_packed, uint64_t packed_cap,
+                        uint64_t* d_sizes, uint64_t* d_prefix);
+TB200_API int tb200_decode_streams(tb200_ctx* ctx, int n, const uint8_t* headers, const uint8_t* d_packed, const uint64_t* offsets,
+                        const uint64_t* sizes, void* const* d_out, uint32_t* d_status);
+
 /* ---- multi-GPU: chunk-sharded streams; one process per GPU, NCCL loaded at run time ----
  * A stream is cut into contiguous chunk-aligned shares, one per rank.  Every rank encodes its share
  * with the ordinary kernels (no data-path collective); an all-gather exchanges the compressed sizes;

@@ -541,3 +541,46 @@ def test_lz4_noisy_and_short_run_planes(dev, oracle):
         for log2c in (12, 14):
             g = _check_lz4_both_ways(dev, oracle, ty, arr, log2c)
             assert len(g) < arr.nbytes * 1.01 + 64, (ty, log2c, len(g), arr.nbytes)
+
+
+def test_batched_streams_equal_the_per_stream_path():
+    """tb200_encode_streams / tb200_decode_streams (BASELINE C5: many small meshes): the packed batch is
+    byte for byte the concatenation of what tb200_encode_stream produces stream by stream, and it
+    decodes to the inputs."""
+    import trico_b200
+    from trico_b200 import STREAM_DTYPES
+    from trico_b200.synth import grid_mesh
+    dev = trico_b200.Device(0)
+    rng = np.random.default_rng(11)
+    items = []
+    for m, side in enumerate((9, 33, 40, 64, 101, 7, 150)):
+        v, t = grid_mesh(side, side, jitter=1.0, seed=50 + m)
+        nv = v.shape[0]
+        items += [(1, v, nv), (3, t, t.shape[0]), (15, np.ascontiguousarray(v[:, 2]), nv),
+                  (17, (np.arange(nv) >> 4).astype(np.uint8), nv), (18, (v[:, 2] * 1000 + 20000).astype(np.uint16), nv),
+                  (20, (np.arange(nv, dtype=np.uint64) | (np.uint64(m) << np.uint64(32))), nv)]
+    bufs = [dev.upload(np.ascontiguousarray(a, dtype=STREAM_DTYPES[ty])) for ty, a, _ in items]
+    batch = dev.Batch([ty for ty, _, _ in items], [b.ptr for b in bufs], [c for _, _, c in items])
+    n = batch.n
+    cap = dev.batch_arena_bytes(batch)
+    arena, packed = dev.alloc(cap), dev.alloc(cap)
+    d_sizes, d_prefix, d_status = dev.alloc(8 * n), dev.alloc(8 * (2 * n + 2)), dev.alloc(64)
+    dev.lib.tb200_memset_d.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64]
+    dev.lib.tb200_memset_d(dev.ctx, C.c_void_p(d_status.ptr), 0, 64)
+    dev.encode_streams(batch, arena.ptr, cap, packed.ptr, cap, d_sizes.ptr, d_prefix.ptr)
+    dev.sync()
+    sizes = dev.download(d_sizes.ptr, 8 * n).view(np.uint64)
+    prefix = dev.download(d_prefix.ptr, 8 * (n + 1)).view(np.uint64)
+    blob = dev.download(packed.ptr, int(prefix[n])).tobytes()
+    want = b"".join(dev.encode_stream(ty, a, c) for ty, a, c in items)
+    assert blob == want
+    assert [int(x) for x in prefix[:n]] == list(np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(int))
+    outs = [dev.alloc(np.ascontiguousarray(a, dtype=STREAM_DTYPES[ty]).nbytes + 64) for ty, a, _ in items]
+    headers = b"".join(blob[int(o):int(o) + 15] for o in prefix[:n])
+    dev.decode_streams(headers, packed.ptr, [int(x) for x in prefix[:n]], [int(x) for x in sizes], [o.ptr for o in outs], d_status.ptr)
+    dev.sync()
+    assert int(dev.download(d_status.ptr, 4).view(np.uint32)[0]) == 0
+    for (ty, a, c), o in zip(items, outs):
+        a = np.ascontiguousarray(a, dtype=STREAM_DTYPES[ty])
+        assert dev.download(o.ptr, a.nbytes).tobytes() == a.tobytes()
+    dev.close()

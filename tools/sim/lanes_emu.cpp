@@ -74,7 +74,7 @@ int main(int argc, char** argv)
     if (nbytes[0] > n + n / 255 + 16) { fprintf(stderr, "block %zu: %u bytes exceed the LZ4 bound\n", nblocks, nbytes[0]); rc = 1; }
     const long d = lz4_decode_plain(out.data(), nbytes[0], back.data(), n);
     if (d != (long)n || memcmp(back.data(), in.data() + b0, n) != 0) { fprintf(stderr, "block %zu: round trip failed (decoder returned %ld for %u bytes)\n", nblocks, d, n); rc = 1; }
-    if (fo) fprintf(fo, "%u\n", nbytes[0]);
+    if (fo) { fprintf(fo, "%u\n", nbytes[0]); fflush(fo); }
     total += nbytes[0];
     if (warp.mismatches.load()) { fprintf(stderr, "block %zu: lanes left the common path\n", nblocks); rc = 1; break; }
     }

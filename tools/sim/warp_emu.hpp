@@ -88,7 +88,7 @@ template <typename T> static inline T emu_shfl(int site, T v, int src)
   return r;
   }
 static inline int emu_lane() { return (int)(threadIdx.x & 31); }
-#define __syncwarp() emu_syncwarp(__LINE__)
+#define __syncwarp(...) emu_syncwarp(__LINE__)
 #define __ballot_sync(mask_, pred_) emu_ballot(__LINE__, (pred_))
 #define __any_sync(mask_, pred_) (emu_ballot(__LINE__, (pred_)) != 0)
 #define __all_sync(mask_, pred_) (emu_ballot(__LINE__, (pred_)) == 0xffffffffu)

@@ -38,17 +38,22 @@ cases = [
     ("attr u16 (type 18)", 18, np.clip((pz + 5.5) * 5000, 0, 65535).astype(np.uint16), nv),
     ("attr u64 (type 20)", 20, np.arange(nv, dtype=np.uint64) | (np.uint64(7) << 32), nv),
 ]
+only = os.environ.get("ONLY")
 for name, ty, data, cnt in cases:
+    if only and str(ty) not in only.split(","): continue
     data = np.ascontiguousarray(data, dtype=trico_b200.STREAM_DTYPES[ty])
     log2c = dev.lib.tb200_default_log2_chunk(ty, cnt)
     bound = dev.lib.tb200_v1_stream_bound(ty, cnt, log2c)
     d_in, d_out, d_sz, d_back = dev.upload(data), dev.alloc(bound), dev.alloc(64), dev.alloc(data.nbytes + 64)
     def enc(): dev.encode_stream_device(ty, d_in.ptr, cnt, d_out.ptr, bound, d_sz.ptr, log2c)
+    if only: print("encode", name, flush=True)
     enc(); dev.sync()
+    if only: print("encoded", flush=True)
     nbytes = int(dev.download(d_sz.ptr, 8).view(np.uint64)[0])
     hdr = dev.download(d_out.ptr, 16).tobytes()
     def dec(): dev.decode_stream_device(hdr, d_out.ptr, nbytes, d_back.ptr)
     dec(); dev.sync()
+    if only: print("decoded", nbytes, flush=True)
     if not os.environ.get("NOVERIFY"): assert dev.download(d_back.ptr, data.nbytes).tobytes() == data.tobytes(), name
     res = []
     for f in (enc, dec):

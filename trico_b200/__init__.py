@@ -77,6 +77,9 @@ def load() -> C.CDLL:
         "tb200_event_record": (C.c_int, [_vp, _vp]),
         "tb200_event_elapsed_ms": (C.c_float, [_vp, _vp]),
         "trico_b200_last_error": (C.c_char_p, []),
+        "tb200_batch_arena_bytes": (C.c_uint64, [C.c_int, _vp, _vp]),
+        "tb200_encode_streams": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp, _vp]),
+        "tb200_decode_streams": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
         "tb200_comm_unique_id": (C.c_int, [_vp]),
         "tb200_comm_create": (_vp, [_vp, C.c_int, C.c_int, _vp]),
         "tb200_comm_destroy": (None, [_vp]),
@@ -193,6 +196,32 @@ class Device:
         for b in (d_in, d_out, d_sz):
             b.free()
         return out
+
+    # -- batches of streams (many small meshes) --------------------------------------------------
+    class Batch:
+        """host-side description of a batch: arrays the C entry points read (kept alive here)"""
+
+        def __init__(self, types, ptrs, counts):
+            self.n = len(types)
+            self.types = (C.c_int * self.n)(*types)
+            self.counts = (C.c_uint32 * self.n)(*counts)
+            self.ptrs = (C.c_void_p * self.n)(*ptrs)
+
+    def batch_arena_bytes(self, batch) -> int:
+        return self.lib.tb200_batch_arena_bytes(batch.n, batch.types, batch.counts)
+
+    def encode_streams(self, batch, d_arena: int, arena_cap: int, d_packed: int, packed_cap: int, d_sizes: int, d_prefix: int):
+        """asynchronous; d_sizes: n u64, d_prefix: 2n + 2 u64 (offsets of the streams in d_packed, total, scratch)"""
+        self._ck(self.lib.tb200_encode_streams(self.ctx, batch.n, batch.types, batch.ptrs, batch.counts, _vp(d_arena), arena_cap,
+                                               _vp(d_packed), packed_cap, _vp(d_sizes), _vp(d_prefix)))
+
+    def decode_streams(self, headers: bytes, d_packed: int, offsets, sizes, out_ptrs, d_status: int):
+        n = len(offsets)
+        hb = (C.c_uint8 * (15 * n)).from_buffer_copy(headers)
+        off = (C.c_uint64 * n)(*offsets)
+        sz = (C.c_uint64 * n)(*sizes)
+        outs = (C.c_void_p * n)(*out_ptrs)
+        self._ck(self.lib.tb200_decode_streams(self.ctx, n, hb, _vp(d_packed), off, sz, outs, _vp(d_status)))
 
     # -- multi-GPU: chunk-sharded streams (one process per GPU) -------------------------------
     def shard_range(self, stream_type: int, count: int, rank: int, world: int, log2_chunk: int = 0):

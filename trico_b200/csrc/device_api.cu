@@ -41,6 +41,10 @@ struct tb200_ctx
   size_t big_bytes;
   uint64_t launches;
   int max_smem_optin;
+  // batches of streams run on several CUDA streams: sub-contexts, created on first use (device_api_misc.inc)
+  tb200_ctx* sub[7];
+  int nsub;
+  cudaEvent_t ev_fork, ev_join[7];
   };
 
 extern "C" int tb200_device_count(void)
@@ -76,6 +80,8 @@ extern "C" void tb200_ctx_destroy(tb200_ctx* c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < c->nsub; ++i) tb200_ctx_destroy(c->sub[i]);
+  if (c->nsub) { cudaEventDestroy(c->ev_fork); for (int i = 0; i < c->nsub; ++i) cudaEventDestroy(c->ev_join[i]); }
   if (c->ws) cudaFree(c->ws);
   if (c->big) cudaFree(c->big);
   if (c->own_stream) cudaStreamDestroy(c->stream);

@@ -1219,12 +1219,25 @@ __device__ __forceinline__ int lz4_decode_batch(const uint8_t* ib, uint8_t* ob, 
   // the matches of earlier sequences this lane's source overlaps: [s, e) = the part of the source
   // that this lane does not produce itself, against every earlier match [dst_j, dst_j + ml_j)
   const uint32_t s_lo = dst - off, s_hi = act ? min(s_lo + my_ml, dst) : 0u;
-  unsigned waits = 0;
-  for (int j = 0; j < nseq - 1; ++j)
+  // the earlier matches are sorted by position, so those that overlap [s_lo, s_hi) are a range of
+  // lanes [jlo, jhi): jlo = the first match that ends behind s_lo, jhi = the first one that starts at
+  // or behind s_hi - two binary searches over the lanes' registers
+  const uint32_t m_end = dst + my_ml;
+  uint32_t jlo = 0, jhi = 0;
     {
-    const uint32_t aj = __shfl_sync(FULL, dst, j), bj = aj + __shfl_sync(FULL, my_ml, j);
-    if ((int)lane > j && aj < s_hi && bj > s_lo) waits |= 1u << j;
+    uint32_t lo = 0, hi = (uint32_t)nseq, lo2 = 0, hi2 = (uint32_t)nseq;
+#pragma unroll
+    for (int step = 0; step < 6; ++step)
+      {
+      const uint32_t mid = (lo + hi) >> 1, mid2 = (lo2 + hi2) >> 1;
+      const uint32_t be = __shfl_sync(FULL, m_end, mid & 31u), as = __shfl_sync(FULL, dst, mid2 & 31u);
+      if (lo < hi) { if (be <= s_lo) lo = mid + 1u; else hi = mid; }
+      if (lo2 < hi2) { if (as < s_hi) lo2 = mid2 + 1u; else hi2 = mid2; }
+      }
+    jlo = lo; jhi = lo2;
     }
+  if (jhi > lane) jhi = lane;                                // only earlier sequences
+  const unsigned waits = (act && jhi > jlo) ? (((jhi >= 32u ? 0u : (1u << jhi)) - 1u) & ~((1u << jlo) - 1u)) : 0u;
   bool open = act;
   for (;;)
     {

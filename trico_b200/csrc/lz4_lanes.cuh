@@ -27,13 +27,26 @@
 
 namespace tb200 {
 
-#ifdef TB200_LZ4L_DEBUG
+#if defined(TB200_LZ4L_DEBUG) || defined(TB200_LZ4L_WATCHONLY)
+#define TB200_LZ4L_PROBE 1
 __device__ volatile unsigned int* g_lz4l_host;      // mapped page-locked host memory: survives a faulting kernel
+__device__ unsigned int g_lz4l_dbg[8];
+__device__ unsigned int g_lz4l_cur[1 << 16];        // chunk id a CTA is working on
+#define LZ4L_REPORT(code, val) do { if (atomicCAS(&g_lz4l_dbg[0], 0u, (unsigned)(code)) == 0u) { g_lz4l_dbg[1] = (unsigned)(val); g_lz4l_dbg[2] = lane_id(); g_lz4l_dbg[3] = g_lz4l_cur[blockIdx.x & 0xffffu]; \
+  if (g_lz4l_host) { g_lz4l_host[1] = (unsigned)(val); g_lz4l_host[2] = lane_id(); g_lz4l_host[3] = g_lz4l_cur[blockIdx.x & 0xffffu]; g_lz4l_host[0] = (unsigned)(code); __threadfence_system(); } } } while (0)
+#define LZ4L_WATCH(counter, limit, code, val) do { if (++(counter) > (limit)) { LZ4L_REPORT(code, val); return 0; } } while (0)
+__device__ unsigned int g_lz4l_target[2] = {0xffffffffu, 0u};      // chunk id and lane whose parse is traced into the host page
+#define LZ4L_TRACE(slot, v) do { if (g_lz4l_host && g_lz4l_cur[blockIdx.x & 0xffffu] == g_lz4l_target[0] && lane_id() == g_lz4l_target[1]) { g_lz4l_host[16 + (slot)] = (unsigned)(v); } } while (0)
+#define LZ4L_TRACE_FENCE() __threadfence_system()
+#define LZ4L_CONVERGED(code) do { const unsigned am_ = __activemask(); if (am_ != FULL) LZ4L_REPORT(code, am_); } while (0)
+#else
+#define LZ4L_WATCH(counter, limit, code, val) do { } while (0)
+#define LZ4L_CONVERGED(code) do { } while (0)
+#define LZ4L_TRACE(slot, v) do { } while (0)
+#define LZ4L_TRACE_FENCE() do { } while (0)
 #endif
 #ifdef TB200_LZ4L_DEBUG
-__device__ unsigned int g_lz4l_dbg[8];
-#define LZ4L_CHECK(cond, code, val) do { if (!(cond)) { if (atomicCAS(&g_lz4l_dbg[0], 0u, (unsigned)(code)) == 0u) { g_lz4l_dbg[1] = (unsigned)(val); g_lz4l_dbg[2] = lane_id(); g_lz4l_dbg[3] = blockIdx.x; \
-  if (g_lz4l_host) { g_lz4l_host[1] = (unsigned)(val); g_lz4l_host[2] = lane_id(); g_lz4l_host[3] = blockIdx.x; g_lz4l_host[0] = (unsigned)(code); __threadfence_system(); } } } } while (0)
+#define LZ4L_CHECK(cond, code, val) do { if (!(cond)) LZ4L_REPORT(code, val); } while (0)
 #define LZ4L_BAD(cond) (!(cond))
 #else
 #define LZ4L_CHECK(cond, code, val) do { } while (0)
@@ -43,6 +56,10 @@ __device__ unsigned int g_lz4l_dbg[8];
 #ifndef LZ4L_EMIT
 #define LZ4L_EMIT lz4_emit_bytes
 #endif
+#ifndef LZ4L_BOUNDS
+#define LZ4L_BOUNDS 32
+#endif
+#define LZ4L_HARD() __syncwarp()
 #ifndef LZ4L_LAZY
 #define LZ4L_LAZY 1
 #endif
@@ -119,7 +136,7 @@ __device__ __forceinline__ uint32_t lz4_emit_bytes(DstPtr dst, uint32_t op, cons
 #define LZ4L_INLINE __forceinline__
 #endif
 template <typename DstPtr>
-__device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* T, uint8_t* own, uint8_t* regions, uint8_t* stage)
+__device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* T, uint8_t* own, uint8_t* regions, uint8_t* stage, const unsigned fm = FULL)
   {
   constexpr int HLOG = LZ4L_HLOG;
   const unsigned lane = lane_id();
@@ -129,7 +146,7 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
     {
     for (uint32_t i = lane; i < (2u << HLOG); i += 32) T[i] = 0;
     for (uint32_t i = lane; i < (32u << LZ4L_OWNBITS) / 4u; i += 32) reinterpret_cast<uint32_t*>(own)[i] = 0;   // (what was here before must not steer the parse)
-    __syncwarp();
+    __syncwarp(fm);
     const uint32_t mflimit = n - LZ4_MFLIMIT, matchlimit = n - LZ4_LASTLITERALS;
     uint8_t* const reg = regions + lane * LZ4L_REGION;
     uint8_t* const myown = own + lane;               // entry e of this lane: myown[32 * e]
@@ -154,6 +171,7 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
       auto commit = [&](uint32_t q, uint32_t c, uint32_t ml)
         {
         const uint32_t off = q - c;
+        LZ4L_TRACE(18, q); LZ4L_TRACE(19, (c << 16) | ml); LZ4L_TRACE(20, 0xdead0003u); LZ4L_TRACE_FENCE();
         LZ4L_CHECK(q >= anchor && q + ml <= end && c < q && ml >= 4u && q - anchor <= LZ4L_S && anchor >= sub, 1, (q << 16) | ml);
         if (nseq == 0) { f_q = q; f_ml = ml; f_off = off; }
         else
@@ -162,18 +180,23 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
           rbytes += lz4_put_seq(reg + rbytes, src, anchor, q - anchor, off, ml);
           }
         ++nseq;
+        LZ4L_TRACE(20, 0xdead0004u); LZ4L_TRACE_FENCE();
         anchor = q + ml;
         if (ml > best_ml) { best_ml = ml; best_off = off; }
         };
 
+      [[maybe_unused]] uint32_t watch_main = 0, watch_lost = 0, watch_stitch = 0;
       for (;;)
         {
+        LZ4L_WATCH(watch_main, 8192u, 9, pos);
+        LZ4L_HARD();
+        LZ4L_CONVERGED(20);
         // (No lane-divergent code between the end of an iteration and these votes: a pending match
         // that has nothing left to be compared with is committed in the parse section below, and
         // its lane probes again in the next iteration.)
         const bool can = mine && pos <= mflimit && pos + LZ4_MINMATCH <= end;
-        if (__ballot_sync(FULL, can || pend) == 0) break;
-        const unsigned probing = __ballot_sync(FULL, can);
+        if (__ballot_sync(fm, can || pend) == 0) break;
+        const unsigned probing = __ballot_sync(fm, can);
         const uint32_t stride = 1u + (misses >> 6);
         // ---- candidates ----
         uint32_t seq = 0, h = 0, ho = 0;
@@ -195,16 +218,21 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
           LZ4L_CHECK(pos + 4u <= n && h < (1u << HLOG) && ho < 32u && c[1] < n && c[2] < n && c[3] < n, 5, pos);
           }
         // ---- inserts: after every look-up of the step; the highest position of a bucket wins ----
-        __syncwarp();
+        LZ4L_CONVERGED(23);
+        LZ4L_HARD();
         if (can) { myown[32u * ho] = (uint8_t)(pos - sub); Tc[h] = (uint16_t)pos; }
-        __syncwarp();
+        __syncwarp(fm);
         for (;;)
           {
           const bool lost = can && Tc[h] < (uint16_t)pos;
-          if (!__any_sync(FULL, lost)) break;
+          if (!__any_sync(fm, lost)) break;
+          LZ4L_WATCH(watch_lost, 100000u, 10, pos);
           if (lost) Tc[h] = (uint16_t)pos;
-          __syncwarp();
+          LZ4L_HARD();
           }
+        LZ4L_TRACE(0, w0); LZ4L_TRACE(1, pos); LZ4L_TRACE(2, anchor); LZ4L_TRACE(3, (unsigned)can | (pend << 1) | (run[0] << 4) | (run[1] << 5) | (run[2] << 6) | (run[3] << 7));
+        LZ4L_TRACE(4, c[0]); LZ4L_TRACE(5, c[1]); LZ4L_TRACE(6, c[2]); LZ4L_TRACE(7, c[3]); LZ4L_TRACE(8, lim); LZ4L_TRACE(9, end); LZ4L_TRACE(10, nseq); LZ4L_TRACE(11, rbytes);
+        LZ4L_TRACE(12, p_q); LZ4L_TRACE(13, p_c); LZ4L_TRACE(14, p_ml); LZ4L_TRACE(15, watch_main); LZ4L_TRACE(20, 0xdead0001u); LZ4L_TRACE_FENCE();
         // ---- match lengths, four bytes per step, all candidates side by side; the longest wins, the nearest on a tie ----
         uint32_t ml = 0, mc = 0;
         if (can && (run[0] || run[1] || run[2] || run[3]))
@@ -232,54 +260,57 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
             }
           }
         // ---- the parse ----
-        bool hit = false;
+        LZ4L_TRACE(16, ml); LZ4L_TRACE(17, mc); LZ4L_TRACE(20, 0xdead0002u); LZ4L_TRACE_FENCE();
+        LZ4L_CONVERGED(24);
+        bool hit = false, fin = false;                   // fin: the match in p_q/p_c/p_ml is final (ONE commit site: see DESIGN.md)
         if (can)
           {
           if (pend)
             {
             hit = true;
             if (ml > p_ml) { p_q = pos; p_c = mc; p_ml = ml; pos += 1u; }              // the later match is longer: the pending one's first byte becomes a literal
-            else { commit(p_q, p_c, p_ml); pend = false; pos = anchor; }
+            else fin = true;
             }
           else if (ml >= LZ4_MINMATCH)
             {
             hit = true;
             uint32_t q = pos, cc = mc;
             while (q > anchor && cc > 0u && src[q - 1u] == src[cc - 1u]) { --q; --cc; ++ml; }   // backward extension (lz4.c:947-950)
-            if (LZ4L_LAZY && q == pos && pos + 1u <= mflimit && pos + 1u + LZ4_MINMATCH <= end) { pend = true; p_q = q; p_c = cc; p_ml = ml; pos += 1u; }
-            else { commit(q, cc, ml); pos = anchor; }
+            p_q = q; p_c = cc; p_ml = ml;
+            if (LZ4L_LAZY && q == pos && pos + 1u <= mflimit && pos + 1u + LZ4_MINMATCH <= end) { pend = true; pos += 1u; }
+            else fin = true;
             }
           else pos += stride;
           }
-        else if (pend)
-          { // nothing left to compare the pending match with
-          hit = true;
-          commit(p_q, p_c, p_ml);
-          pend = false;
-          pos = anchor;
-          }
+        else if (pend) { hit = true; fin = true; }       // nothing left to compare the pending match with
+        if (fin) { commit(p_q, p_c, p_ml); pend = false; pos = anchor; }
 #ifdef LZ4L_SYNC_EVERY
-        __syncwarp();
+        __syncwarp(fm);
 #endif
-        misses = __any_sync(FULL, hit) ? 0u : misses + (uint32_t)__popc(probing);
+        LZ4L_HARD();
+        LZ4L_CONVERGED(25);
+        misses = __any_sync(fm, hit) ? 0u : misses + (uint32_t)__popc(probing);
         }
 
       // ---- stitch the wave ----
-      __syncwarp();
+      LZ4L_HARD();
+      LZ4L_CONVERGED(21);
       const bool has = nseq != 0u;
-      const unsigned N = __ballot_sync(FULL, has);
+      const unsigned N = __ballot_sync(fm, has);
       if (N != 0u)
         {
         const unsigned below = N & lt;
-        uint32_t prev_end = __shfl_sync(FULL, anchor, below ? 31 - __clz((int)below) : 0);
+        uint32_t prev_end = __shfl_sync(fm, anchor, below ? 31 - __clz((int)below) : 0);
         if (!below) prev_end = lastend;
         const uint32_t flit = has ? f_q - prev_end : 0u;                                // literals of the lane's first sequence
         LZ4L_CHECK(!has || (f_q >= prev_end && f_q < n && prev_end <= n && f_ml >= 4u && f_ml <= 2u * LZ4L_S && f_off >= 1u && f_off <= f_q), 8, (f_q << 16) | prev_end);
         const uint32_t fsz = has ? lz4_seq_bytes(flit, f_ml) : 0u;
-        const unsigned big = __ballot_sync(FULL, has && flit > LZ4L_SHORTLIT);
+        const unsigned big = __ballot_sync(fm, has && flit > LZ4L_SHORTLIT);
         unsigned todo = N;
         while (todo != 0u)
           {
+          LZ4L_WATCH(watch_stitch, 256u, 11, todo);
+          LZ4L_CONVERGED(22);
           // the lanes up to the first one with a long literal run go through the staging buffer
           const unsigned b = big & todo;
           const unsigned seg = b ? (todo & ((1u << (__ffs((int)b) - 1)) - 1u)) : todo;
@@ -291,10 +322,10 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
               {
-              const uint32_t up = __shfl_up_sync(FULL, incl, o);
+              const uint32_t up = __shfl_up_sync(fm, incl, o);
               if (lane >= (unsigned)o) incl += up;
               }
-            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            const uint32_t total = __shfl_sync(fm, incl, 31);
             LZ4L_CHECK(total <= LZ4L_STAGE, 3, total);
             LZ4L_CHECK(op + total <= n + n / 255u + 16u, 4, op + total);
             LZ4L_CHECK(!in || (flit <= LZ4L_SHORTLIT && rbytes <= LZ4L_REGION && prev_end + flit <= n), 6, (flit << 16) | rbytes);
@@ -305,34 +336,34 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
               o += lz4_put_seq(o, src, prev_end, flit, f_off, f_ml);
               for (uint32_t j = 0; j < rbytes; ++j) o[j] = reg[j];
               }
-            __syncwarp();
+            LZ4L_HARD();
 #ifndef LZ4L_NOEMIT
             for (uint32_t i = lane; i < total; i += 32) dst[op + i] = stage[i];
 #endif
-            __syncwarp();
+            __syncwarp(fm);
             op += total;
             todo &= ~seg;
             }
           if (b)
             { // a first sequence behind a long literal run: the whole warp writes it
             const int L = __ffs((int)b) - 1;
-            LZ4L_CHECK(__shfl_sync(FULL, prev_end, L) + __shfl_sync(FULL, flit, L) <= n && op + __shfl_sync(FULL, flit, L) + 70u <= n + n / 255u + 16u, 7, __shfl_sync(FULL, flit, L));
-            if (LZ4L_BAD(__shfl_sync(FULL, prev_end, L) + __shfl_sync(FULL, flit, L) <= n && op + __shfl_sync(FULL, flit, L) + 70u <= n + n / 255u + 16u)) return 0;
+            LZ4L_CHECK(__shfl_sync(fm, prev_end, L) + __shfl_sync(fm, flit, L) <= n && op + __shfl_sync(fm, flit, L) + 70u <= n + n / 255u + 16u, 7, __shfl_sync(fm, flit, L));
+            if (LZ4L_BAD(__shfl_sync(fm, prev_end, L) + __shfl_sync(fm, flit, L) <= n && op + __shfl_sync(fm, flit, L) + 70u <= n + n / 255u + 16u)) return 0;
 #ifndef LZ4L_NOBIG
-            op = LZ4L_EMIT(dst, op, src, __shfl_sync(FULL, prev_end, L), __shfl_sync(FULL, flit, L), __shfl_sync(FULL, f_off, L), __shfl_sync(FULL, f_ml, L));
+            op = LZ4L_EMIT(dst, op, src, __shfl_sync(fm, prev_end, L), __shfl_sync(fm, flit, L), __shfl_sync(fm, f_off, L), __shfl_sync(fm, f_ml, L));
 #endif
-            const uint32_t rb = __shfl_sync(FULL, rbytes, L);
+            const uint32_t rb = __shfl_sync(fm, rbytes, L);
             const uint8_t* rL = regions + (uint32_t)L * LZ4L_REGION;
-            __syncwarp();
+            __syncwarp(fm);
 #ifndef LZ4L_NOEMIT
             for (uint32_t i = lane; i < rb; i += 32) dst[op + i] = rL[i];
 #endif
-            __syncwarp();
+            __syncwarp(fm);
             op += rb;
             todo &= ~(1u << L);
             }
           }
-        lastend = __shfl_sync(FULL, anchor, 31 - __clz((int)N));
+        lastend = __shfl_sync(fm, anchor, 31 - __clz((int)N));
         }
       // the next wave's repeat offset: that of this wave's longest match
         {
@@ -340,12 +371,12 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
           {
-          const uint32_t om = __shfl_xor_sync(FULL, bm, o), oo = __shfl_xor_sync(FULL, bo, o);
+          const uint32_t om = __shfl_xor_sync(fm, bm, o), oo = __shfl_xor_sync(fm, bo, o);
           if (om > bm || (om == bm && oo < bo)) { bm = om; bo = oo; }
           }
         rep = bo;
         }
-      __syncwarp();
+      __syncwarp(fm);
       }
     }
 #ifdef LZ4L_NOFINAL
@@ -372,10 +403,11 @@ struct Lz4DenseArgs
   const uint32_t* list;     // chunk ids handed over
   const uint32_t* count;    // how many
   uint32_t* ticket;         // zeroed
+  unsigned full;            // 0xffffffff, as a run-time value (see the kernel)
   };
 
 template <int WB>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(LZ4L_BOUNDS)
 lz4_encode_dense_kernel(const Lz4DenseArgs a)
   {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -399,6 +431,10 @@ lz4_encode_dense_kernel(const Lz4DenseArgs a)
     if (t >= count) break;
 #endif
     const uint64_t g = a.list[t];
+#ifdef TB200_LZ4L_PROBE
+    if (lane == 0) g_lz4l_cur[blockIdx.x & 0xffffu] = (unsigned)g;
+    __syncwarp();
+#endif
     const uint64_t k = g / WB;
     const uint32_t p = (uint32_t)(g % WB);
     const uint64_t lo = k << a.log2B;
@@ -434,7 +470,7 @@ lz4_encode_dense_kernel(const Lz4DenseArgs a)
       for (uint32_t i = lane; i < cnt; i += 32) buf[i] = gin[(size_t)i * WB + p];
     for (uint32_t i = lane; i < LZ4L_PAD; i += 32) buf[cnt + i] = 0;
     __syncwarp();
-    const uint32_t nbytes = lz4_compress_lanes(buf, cnt, a.scratch + g * a.slot, T, own, regions, stage);
+    const uint32_t nbytes = lz4_compress_lanes(buf, cnt, a.scratch + g * a.slot, T, own, regions, stage, a.full);
     if (lane == 0)
       {
       uint8_t* sz = a.sizes + 2 * g;
