@@ -6,6 +6,7 @@
 #include "fpc.cuh"
 #include "lz4.cuh"
 #include "lz4_lanes.cuh"
+#include "lz4_multi.cuh"
 #include "planes.cuh"
 
 #include <stdio.h>

@@ -168,6 +168,19 @@ __device__ __forceinline__ uint32_t lz4_emit_run(DstPtr dst, uint32_t n, uint32_
 #define TB200_LZ4_DENSE_OUT 9u         // ... while the output stays above TB200_LZ4_DENSE_OUT tenths of the input
 #endif
 constexpr uint32_t LZ4_SRC_PAD = 576;    // zeroed bytes the compressor may read past the block end (512-byte match extension steps)
+// A block that saves less than 1/64 of its bytes is written STORED (one literal run): noise planes
+// (the low bytes of colours, heights, jittered indices) otherwise come out as a few hundred useless
+// sequences that cost the decoder a thousand cycles each - and a stored plane needs no decoder at
+// all (K6M reads it straight from the payload).  Costs at most 1.6 % of ratio on such a plane.
+__host__ __device__ __forceinline__ bool lz4_not_worth(uint32_t nbytes, uint32_t cnt)
+  {
+  return cnt >= 64u && nbytes + (cnt >> 6) >= cnt;
+  }
+__host__ __device__ __forceinline__ uint32_t lz4_literal_run_bytes(uint32_t nlit)
+  { // token, length bytes, literals
+  return 1u + (nlit >= 15u ? (nlit - 15u) / 255u + 1u : 0u) + nlit;
+  }
+
 constexpr uint32_t LZ4_ENC_STAGE = 128;  // per-warp staging bytes for the sequences of one window (lz4_compress_warp)
 constexpr uint32_t LZ4_WIN_CAP = 36;     // match lengths are measured up to this inside a window; longer ones take the warp-wide extension
 
@@ -520,6 +533,7 @@ long_match:
       TB200_EPH(3);
       }
     }
+  if (lz4_not_worth(op + lz4_literal_run_bytes(n - anchor), n)) { op = 0; anchor = 0; }     // stored: the block becomes one literal run
   op = lz4_emit(dst, op, src, anchor, n - anchor, 0, 0);
   TB200_EPH(4);
   if (dbg && lane == 0) for (int i = 0; i < 5; ++i) atomicAdd(dbg + i, (unsigned long long)acc_ph[i]);

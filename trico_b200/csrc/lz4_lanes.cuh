@@ -382,6 +382,7 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
 #ifdef LZ4L_NOFINAL
   return op;
 #else
+  if (lz4_not_worth(op + lz4_literal_run_bytes(n - lastend), n)) { op = 0; lastend = 0; }      // stored: the block becomes one literal run
   return lz4_emit(dst, op, src, lastend, n - lastend, 0, 0);
 #endif
   }
