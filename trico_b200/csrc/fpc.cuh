@@ -1200,6 +1200,8 @@ fpc_decode_legacy_kernel(const FpcLegacyDecodeArgs a)
   using TR = FpcTraits<W>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* ring = smem_raw;                                        // FPC_LEGACY_RING bytes
+  __shared__ W sh_x[32], sh_v[32];
+  __shared__ uint32_t sh_u2[32];
   const unsigned c = blockIdx.x, lane = lane_id();
   const uint8_t* p = a.streams[c];
   const int e1 = (p[0] >> 4) << 1, e2 = (p[0] & 15) << 1;          // fpc.c:214-217
@@ -1270,18 +1272,24 @@ fpc_decode_legacy_kernel(const FpcLegacyDecodeArgs a)
     W x = 0;
     for (uint32_t b = 0; b < my_nb; ++b) x = (W)(x << 8) | (W)rb(my_at + b);
     __syncwarp();
-    // the chain: lane 0 only
-    W mine = 0;
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j)
+    // the chain: lane 0 only.  Residuals and predictor choices go through shared memory (their reads
+    // do not depend on the chain, so the unrolled loop has them in registers ahead of time); what is
+    // left per value is the chain itself: two dependent table reads, the xor and the two hash updates.
+    sh_x[lane] = x; sh_u2[lane] = my_use2 ? 1u : 0u;
+    __syncwarp();
+    if (lane == 0)
       {
-      const W xj = __shfl_sync(FULL, x, j);
-      const bool u2 = __shfl_sync(FULL, (int)my_use2, j) != 0;
-      W v = 0;
-      if (lane == 0 && i0 + (uint32_t)j < todo) v = fpc_decode_value<W, 1>(st, xj, u2, T1, T2, e1, e2, m2);
-      v = __shfl_sync(FULL, v, 0);
-      if ((int)lane == j) mine = v;
+      const uint32_t cnt = todo - i0 < 32u ? todo - i0 : 32u;
+      if (cnt == 32u)
+        {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) sh_v[j] = fpc_decode_value<W, 1>(st, sh_x[j], sh_u2[j] != 0u, T1, T2, e1, e2, m2);
+        }
+      else
+        for (uint32_t j = 0; j < cnt; ++j) sh_v[j] = fpc_decode_value<W, 1>(st, sh_x[j], sh_u2[j] != 0u, T1, T2, e1, e2, m2);
       }
+    __syncwarp();
+    const W mine = sh_v[lane];
     if (i0 + lane < todo) out[(size_t)(i0 + lane) * a.stride] = mine;
     // bytes of the values that exist (the pad slots of a last, incomplete group do not matter any more)
     bp = gp;
