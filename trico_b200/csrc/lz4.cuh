@@ -1156,8 +1156,10 @@ __device__ __forceinline__ void lz4_match_warp(uint8_t* buf, uint32_t opm, uint3
 // Up to 32 consecutive SHORT sequences at once (literal run <= LZ4_BATCH_MAXLIT, match <= LZ4_BATCH_MAXMATCH):
 // the regime of real index planes, colour planes and attribute lists, where a sequence is a few
 // bytes and the one-sequence-per-iteration loop below pays ~1000 cycles for each.
-//   1. a walk over the tokens (one shared-memory read per sequence on the dependency chain, every
-//      lane runs it; lane k keeps sequence k)
+//   1. the token walk, speculatively: every lane computes the length of the sequence that WOULD start
+//      at each of its four bytes of a 128-byte window (independent reads), then the chain through the
+//      window is followed with one shuffle per sequence; lane k keeps sequence k.  (A serial walk -
+//      one dependent shared-memory read and ~25 instructions per sequence - was 70 % of the batch.)
 //   2. every lane fetches its own literals and offset, then writes the literals - all input is read
 //      before anything is written: the output of a later sequence may cover the (consumed) input of
 //      an earlier one, in-place margin or not
@@ -1172,37 +1174,69 @@ constexpr uint32_t LZ4_BATCH_MAXLIT = 32;
 __device__ __forceinline__ int lz4_decode_batch(const uint8_t* ib, uint8_t* ob, uint32_t& ip, uint32_t iend, uint32_t& op, uint32_t cap, uint32_t floor = 0)
   {
   const unsigned lane = lane_id();
-  uint32_t sp = ip, o = op;
-  uint32_t my_sp = 0, my_op = 0, my_lit = 0, my_ml = 0;
+  // 1a. speculation: every lane works out, for each of ITS four bytes of the 128-byte window behind
+  //     ip, how long a batchable sequence starting at that byte would be (token, literal length
+  //     byte, match length byte: the same tests as a serial walk makes) - 0 if none could start there.
+  //     The reads are independent of each other; 32 readable bytes follow every block.
+  const uint32_t base = ip + 4u * lane;
+  uint32_t packed = 0;
+  if (base + 8u <= iend + 32u)
+    {
+    const uint32_t w0 = smem_read32(ib, base), w1 = smem_read32(ib, base + 4u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      {
+      const uint32_t q = base + (uint32_t)j;
+      const uint32_t t = (w0 >> (8 * j)) & 0xffu;
+      const uint32_t x = j < 3 ? (w0 >> (8 * (j + 1))) & 0xffu : w1 & 0xffu;
+      uint32_t lit = t >> 4;
+      uint32_t adv = 3u;
+      bool ok = q < iend;
+      if (lit == 15u) { ok = ok && x <= LZ4_BATCH_MAXLIT - 15u; lit += x; ++adv; }      // else: a long literal run
+      adv += lit;
+      ok = ok && q + adv <= iend;                                 // else: the block's last sequence (no match part)
+      if (ok && (t & 15u) == 15u) { ok = (uint32_t)ib[q + adv] <= LZ4_BATCH_MAXMATCH - 19u; ++adv; }   // else: a long match
+      packed |= (ok ? adv : 0u) << (8 * j);
+      }
+    }
+  // 1b. the chain through the window: one shuffle per sequence (the serial walk paid a dependent
+  //     shared-memory read and ~25 instructions for each); lane k keeps sequence k
+  uint32_t cur = 0, my_q = 0, my_adv = 0;
   int nseq = 0;
 #pragma unroll 1
-  for (int k = 0; k < 32; ++k)
+  for (int k = 0; k < 32 && cur < 128u; ++k)
     {
-    if (sp >= iend) break;
-    const uint32_t t = ib[sp];
-    uint32_t lit = t >> 4;
-    const uint32_t mlc = t & 15u;
-    uint32_t adv = 3u;
-    if (lit == 15u)
-      {
-      const uint32_t x = ib[sp + 1u];
-      if (x > LZ4_BATCH_MAXLIT - 15u) break;                // long literal run
-      lit += x; ++adv;
-      }
-    adv += lit;
-    if (sp + adv > iend) break;                              // the block's last sequence (no match part)
-    uint32_t ml = LZ4_MINMATCH + mlc;
-    if (mlc == 15u)
-      {
-      const uint32_t x = ib[sp + adv];
-      if (x > LZ4_BATCH_MAXMATCH - 19u) break;              // long match (or a longer continuation)
-      ml += x; ++adv;
-      }
-    if (o + lit + ml > cap) break;                            // does not fit (a malformed block, or the end of a segment: the caller decides)
-    if ((int)lane == k) { my_sp = sp; my_op = o; my_lit = lit; my_ml = ml; }
-    sp += adv; o += lit + ml; ++nseq;
+    const uint32_t adv = (__shfl_sync(FULL, packed, (int)(cur >> 2)) >> (8u * (cur & 3u))) & 0xffu;
+    if (adv == 0u) break;
+    if ((int)lane == k) { my_q = cur; my_adv = adv; }
+    cur += adv; ++nseq;
     }
   if (nseq == 0) return 0;
+  // 1c. every lane reads the lengths of its own sequence; output positions by a scan
+  const uint32_t my_sp = ip + my_q;
+  uint32_t my_lit = 0, my_ml = 0;
+  if ((int)lane < nseq)
+    {
+    const uint32_t t = ib[my_sp];
+    my_lit = t >> 4;
+    if (my_lit == 15u) my_lit += ib[my_sp + 1u];
+    my_ml = LZ4_MINMATCH + (t & 15u);
+    if ((t & 15u) == 15u) my_ml += ib[my_sp + my_adv - 1u];
+    }
+  uint32_t incl = my_lit + my_ml;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1)
+    {
+    const uint32_t up = __shfl_up_sync(FULL, incl, d);
+    if (lane >= (unsigned)d) incl += up;
+    }
+  const uint32_t my_op = op + incl - (my_lit + my_ml);
+  // a sequence that does not fit ends the batch (a malformed block, or the end of a segment: the caller decides)
+  const unsigned over = __ballot_sync(FULL, (int)lane < nseq && op + incl > cap);
+  if (over) nseq = __ffs((int)over) - 1;
+  if (nseq == 0) return 0;
+  const uint32_t sp = ip + __shfl_sync(FULL, my_q + my_adv, nseq - 1);
+  const uint32_t o = op + __shfl_sync(FULL, incl, nseq - 1);
   const bool act = (int)lane < nseq;
   uint64_t lw[4] = {0, 0, 0, 0};                            // this lane's literals (<= 32 bytes)
   uint32_t off = 0;
