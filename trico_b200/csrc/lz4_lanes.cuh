@@ -56,10 +56,6 @@ __device__ unsigned int g_lz4l_target[2] = {0xffffffffu, 0u};      // chunk id a
 #ifndef LZ4L_EMIT
 #define LZ4L_EMIT lz4_emit_bytes
 #endif
-#ifndef LZ4L_BOUNDS
-#define LZ4L_BOUNDS 32
-#endif
-#define LZ4L_HARD() __syncwarp()
 #ifndef LZ4L_LAZY
 #define LZ4L_LAZY 1
 #endif
@@ -136,7 +132,7 @@ __device__ __forceinline__ uint32_t lz4_emit_bytes(DstPtr dst, uint32_t op, cons
 #define LZ4L_INLINE __forceinline__
 #endif
 template <typename DstPtr>
-__device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* T, uint8_t* own, uint8_t* regions, uint8_t* stage, const unsigned fm = FULL)
+__device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t n, DstPtr dst, uint16_t* T, uint8_t* own, uint8_t* regions, uint8_t* stage)
   {
   constexpr int HLOG = LZ4L_HLOG;
   const unsigned lane = lane_id();
@@ -146,7 +142,7 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
     {
     for (uint32_t i = lane; i < (2u << HLOG); i += 32) T[i] = 0;
     for (uint32_t i = lane; i < (32u << LZ4L_OWNBITS) / 4u; i += 32) reinterpret_cast<uint32_t*>(own)[i] = 0;   // (what was here before must not steer the parse)
-    __syncwarp(fm);
+    __syncwarp();
     const uint32_t mflimit = n - LZ4_MFLIMIT, matchlimit = n - LZ4_LASTLITERALS;
     uint8_t* const reg = regions + lane * LZ4L_REGION;
     uint8_t* const myown = own + lane;               // entry e of this lane: myown[32 * e]
@@ -189,14 +185,14 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
       for (;;)
         {
         LZ4L_WATCH(watch_main, 8192u, 9, pos);
-        LZ4L_HARD();
+        __syncwarp();
         LZ4L_CONVERGED(20);
         // (No lane-divergent code between the end of an iteration and these votes: a pending match
         // that has nothing left to be compared with is committed in the parse section below, and
         // its lane probes again in the next iteration.)
         const bool can = mine && pos <= mflimit && pos + LZ4_MINMATCH <= end;
-        if (__ballot_sync(fm, can || pend) == 0) break;
-        const unsigned probing = __ballot_sync(fm, can);
+        if (__ballot_sync(FULL, can || pend) == 0) break;
+        const unsigned probing = __ballot_sync(FULL, can);
         const uint32_t stride = 1u + (misses >> 6);
         // ---- candidates ----
         uint32_t seq = 0, h = 0, ho = 0;
@@ -219,16 +215,16 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
           }
         // ---- inserts: after every look-up of the step; the highest position of a bucket wins ----
         LZ4L_CONVERGED(23);
-        LZ4L_HARD();
+        __syncwarp();
         if (can) { myown[32u * ho] = (uint8_t)(pos - sub); Tc[h] = (uint16_t)pos; }
-        __syncwarp(fm);
+        __syncwarp();
         for (;;)
           {
           const bool lost = can && Tc[h] < (uint16_t)pos;
-          if (!__any_sync(fm, lost)) break;
+          if (!__any_sync(FULL, lost)) break;
           LZ4L_WATCH(watch_lost, 100000u, 10, pos);
           if (lost) Tc[h] = (uint16_t)pos;
-          LZ4L_HARD();
+          __syncwarp();
           }
         LZ4L_TRACE(0, w0); LZ4L_TRACE(1, pos); LZ4L_TRACE(2, anchor); LZ4L_TRACE(3, (unsigned)can | (pend << 1) | (run[0] << 4) | (run[1] << 5) | (run[2] << 6) | (run[3] << 7));
         LZ4L_TRACE(4, c[0]); LZ4L_TRACE(5, c[1]); LZ4L_TRACE(6, c[2]); LZ4L_TRACE(7, c[3]); LZ4L_TRACE(8, lim); LZ4L_TRACE(9, end); LZ4L_TRACE(10, nseq); LZ4L_TRACE(11, rbytes);
@@ -285,27 +281,27 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
         else if (pend) { hit = true; fin = true; }       // nothing left to compare the pending match with
         if (fin) { commit(p_q, p_c, p_ml); pend = false; pos = anchor; }
 #ifdef LZ4L_SYNC_EVERY
-        __syncwarp(fm);
+        __syncwarp();
 #endif
-        LZ4L_HARD();
+        __syncwarp();
         LZ4L_CONVERGED(25);
-        misses = __any_sync(fm, hit) ? 0u : misses + (uint32_t)__popc(probing);
+        misses = __any_sync(FULL, hit) ? 0u : misses + (uint32_t)__popc(probing);
         }
 
       // ---- stitch the wave ----
-      LZ4L_HARD();
+      __syncwarp();
       LZ4L_CONVERGED(21);
       const bool has = nseq != 0u;
-      const unsigned N = __ballot_sync(fm, has);
+      const unsigned N = __ballot_sync(FULL, has);
       if (N != 0u)
         {
         const unsigned below = N & lt;
-        uint32_t prev_end = __shfl_sync(fm, anchor, below ? 31 - __clz((int)below) : 0);
+        uint32_t prev_end = __shfl_sync(FULL, anchor, below ? 31 - __clz((int)below) : 0);
         if (!below) prev_end = lastend;
         const uint32_t flit = has ? f_q - prev_end : 0u;                                // literals of the lane's first sequence
         LZ4L_CHECK(!has || (f_q >= prev_end && f_q < n && prev_end <= n && f_ml >= 4u && f_ml <= 2u * LZ4L_S && f_off >= 1u && f_off <= f_q), 8, (f_q << 16) | prev_end);
         const uint32_t fsz = has ? lz4_seq_bytes(flit, f_ml) : 0u;
-        const unsigned big = __ballot_sync(fm, has && flit > LZ4L_SHORTLIT);
+        const unsigned big = __ballot_sync(FULL, has && flit > LZ4L_SHORTLIT);
         unsigned todo = N;
         while (todo != 0u)
           {
@@ -322,10 +318,10 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
               {
-              const uint32_t up = __shfl_up_sync(fm, incl, o);
+              const uint32_t up = __shfl_up_sync(FULL, incl, o);
               if (lane >= (unsigned)o) incl += up;
               }
-            const uint32_t total = __shfl_sync(fm, incl, 31);
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
             LZ4L_CHECK(total <= LZ4L_STAGE, 3, total);
             LZ4L_CHECK(op + total <= n + n / 255u + 16u, 4, op + total);
             LZ4L_CHECK(!in || (flit <= LZ4L_SHORTLIT && rbytes <= LZ4L_REGION && prev_end + flit <= n), 6, (flit << 16) | rbytes);
@@ -336,34 +332,34 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
               o += lz4_put_seq(o, src, prev_end, flit, f_off, f_ml);
               for (uint32_t j = 0; j < rbytes; ++j) o[j] = reg[j];
               }
-            LZ4L_HARD();
+            __syncwarp();
 #ifndef LZ4L_NOEMIT
             for (uint32_t i = lane; i < total; i += 32) dst[op + i] = stage[i];
 #endif
-            __syncwarp(fm);
+            __syncwarp();
             op += total;
             todo &= ~seg;
             }
           if (b)
             { // a first sequence behind a long literal run: the whole warp writes it
             const int L = __ffs((int)b) - 1;
-            LZ4L_CHECK(__shfl_sync(fm, prev_end, L) + __shfl_sync(fm, flit, L) <= n && op + __shfl_sync(fm, flit, L) + 70u <= n + n / 255u + 16u, 7, __shfl_sync(fm, flit, L));
-            if (LZ4L_BAD(__shfl_sync(fm, prev_end, L) + __shfl_sync(fm, flit, L) <= n && op + __shfl_sync(fm, flit, L) + 70u <= n + n / 255u + 16u)) return 0;
+            LZ4L_CHECK(__shfl_sync(FULL, prev_end, L) + __shfl_sync(FULL, flit, L) <= n && op + __shfl_sync(FULL, flit, L) + 70u <= n + n / 255u + 16u, 7, __shfl_sync(FULL, flit, L));
+            if (LZ4L_BAD(__shfl_sync(FULL, prev_end, L) + __shfl_sync(FULL, flit, L) <= n && op + __shfl_sync(FULL, flit, L) + 70u <= n + n / 255u + 16u)) return 0;
 #ifndef LZ4L_NOBIG
-            op = LZ4L_EMIT(dst, op, src, __shfl_sync(fm, prev_end, L), __shfl_sync(fm, flit, L), __shfl_sync(fm, f_off, L), __shfl_sync(fm, f_ml, L));
+            op = LZ4L_EMIT(dst, op, src, __shfl_sync(FULL, prev_end, L), __shfl_sync(FULL, flit, L), __shfl_sync(FULL, f_off, L), __shfl_sync(FULL, f_ml, L));
 #endif
-            const uint32_t rb = __shfl_sync(fm, rbytes, L);
+            const uint32_t rb = __shfl_sync(FULL, rbytes, L);
             const uint8_t* rL = regions + (uint32_t)L * LZ4L_REGION;
-            __syncwarp(fm);
+            __syncwarp();
 #ifndef LZ4L_NOEMIT
             for (uint32_t i = lane; i < rb; i += 32) dst[op + i] = rL[i];
 #endif
-            __syncwarp(fm);
+            __syncwarp();
             op += rb;
             todo &= ~(1u << L);
             }
           }
-        lastend = __shfl_sync(fm, anchor, 31 - __clz((int)N));
+        lastend = __shfl_sync(FULL, anchor, 31 - __clz((int)N));
         }
       // the next wave's repeat offset: that of this wave's longest match
         {
@@ -371,12 +367,12 @@ __device__ LZ4L_INLINE uint32_t lz4_compress_lanes(const uint8_t* src, uint32_t 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
           {
-          const uint32_t om = __shfl_xor_sync(fm, bm, o), oo = __shfl_xor_sync(fm, bo, o);
+          const uint32_t om = __shfl_xor_sync(FULL, bm, o), oo = __shfl_xor_sync(FULL, bo, o);
           if (om > bm || (om == bm && oo < bo)) { bm = om; bo = oo; }
           }
         rep = bo;
         }
-      __syncwarp(fm);
+      __syncwarp();
       }
     }
 #ifdef LZ4L_NOFINAL
@@ -404,11 +400,10 @@ struct Lz4DenseArgs
   const uint32_t* list;     // chunk ids handed over
   const uint32_t* count;    // how many
   uint32_t* ticket;         // zeroed
-  unsigned full;            // 0xffffffff, as a run-time value (see the kernel)
   };
 
 template <int WB>
-__global__ void __launch_bounds__(LZ4L_BOUNDS)
+__global__ void __launch_bounds__(32)
 lz4_encode_dense_kernel(const Lz4DenseArgs a)
   {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -471,7 +466,7 @@ lz4_encode_dense_kernel(const Lz4DenseArgs a)
       for (uint32_t i = lane; i < cnt; i += 32) buf[i] = gin[(size_t)i * WB + p];
     for (uint32_t i = lane; i < LZ4L_PAD; i += 32) buf[cnt + i] = 0;
     __syncwarp();
-    const uint32_t nbytes = lz4_compress_lanes(buf, cnt, a.scratch + g * a.slot, T, own, regions, stage, a.full);
+    const uint32_t nbytes = lz4_compress_lanes(buf, cnt, a.scratch + g * a.slot, T, own, regions, stage);
     if (lane == 0)
       {
       uint8_t* sz = a.sizes + 2 * g;

@@ -29,7 +29,7 @@ constexpr int LZ4_DEC_MAXTILES = 4;          // tiles a CTA decodes together at 
 constexpr uint32_t LZ4_DEC_HEAVY = 2048;     // a block this large (bytes) has many sequences: its tile gives up the buffers of its stored planes
 
 template <int WB>
-__global__ void __launch_bounds__(WB * 32, WB == 8 ? 2 : 3)      // what the shared memory of the plane buffers admits
+__global__ void __launch_bounds__(WB * 32, WB == 8 ? 2 : (WB == 4 ? 4 : 8))      // 8 KiB plane blocks (colours, 2- and 8-byte lists) leave shared memory for this many CTAs
 lz4_decode_multi_kernel(const Lz4DecodeArgs a)
   {
   extern __shared__ __align__(16) uint8_t smem_raw[];
