@@ -218,6 +218,7 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
   const unsigned lane = lane_id();
   const unsigned lt = lanemask_lt();
   uint32_t op = 0, anchor = 0;
+  bool give_up = false;
   if (n >= LZ4_MFLIMIT + 1)
     {
     for (uint32_t i = lane; i < (1u << HLOG); i += 32) table[i] = 0;
@@ -225,6 +226,7 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
     const uint32_t mflimit = n - LZ4_MFLIMIT;        // last position where a match may start
     const uint32_t matchlimit = n - LZ4_LASTLITERALS;
     uint32_t p = 0, attempts = 0, nseq = 0;
+    bool quarter_seen = false;
     // Dense mode: data that yields a match every few bytes WITHOUT getting smaller for it (noisy
     // planes: colours, quantised heights - four equal bytes turn up by chance all the time) pays
     // for every sequence twice, here and in the decoder.  Once the sequences of the block average
@@ -249,6 +251,13 @@ __device__ __forceinline__ uint32_t lz4_compress_warp(const uint8_t* src, uint32
       };
     while (p <= mflimit)
       {
+      if (!quarter_seen && p >= (n >> 2) && p >= 1024u)
+        { // Nothing gained on the first quarter of the block: noise (the low planes of colours, heights,
+          // jittered indices).  The block will be stored; searching the rest of it costs this warp
+          // ~2000 cycles per 32 bytes for nothing.
+        quarter_seen = true;
+        if (lz4_not_worth(op + lz4_literal_run_bytes(p - anchor), p)) { give_up = true; break; }
+        }
       const uint32_t stride = 1u + (attempts >> 6);
       uint32_t mq, mc;
       if (stride >= 2u && (attempts & 32u) == 0)
@@ -533,7 +542,7 @@ long_match:
       TB200_EPH(3);
       }
     }
-  if (lz4_not_worth(op + lz4_literal_run_bytes(n - anchor), n)) { op = 0; anchor = 0; }     // stored: the block becomes one literal run
+  if (give_up || lz4_not_worth(op + lz4_literal_run_bytes(n - anchor), n)) { op = 0; anchor = 0; }     // stored: the block becomes one literal run
   op = lz4_emit(dst, op, src, anchor, n - anchor, 0, 0);
   TB200_EPH(4);
   if (dbg && lane == 0) for (int i = 0; i < 5; ++i) atomicAdd(dbg + i, (unsigned long long)acc_ph[i]);
