@@ -214,3 +214,27 @@ def test_ratio_per_stream_type_against_reference_whole_stream(dev, oracle):
     with open(os.path.join(ROOT, "gpurun_out", "ratio_per_stream_type.txt"), "w") as f:
         f.write(text + "\n")
     assert not bad, f"{bad}\n{text}"
+
+
+# ------------------------------------------------ reference-format streams, tile-parallel (K3L)
+@pytest.mark.parametrize("n", [8 * 2048, 8 * 2048 + 1, 16391, 100003, 1_000_000, 3_000_001])
+def test_v0_stream_tile_parallel_is_byte_identical(ours, oracle, n):
+    """trico_compress on long float arrays runs the tile-parallel encoder (fpc_encode_v0_tiles_kernel):
+    the bytes are those of the serial reference algorithm (oracle.fpc_compress = fpc.c:86-210, pinned
+    against the compiled reference in test_oracle.py), for smooth, noisy and special-value data and
+    for two exponent pairs"""
+    rng = np.random.default_rng(n)
+    i = np.arange(n)
+    smooth = (5 * np.sin(0.0037 * i) * np.cos(0.00021 * i) + 0.01 * rng.random(n)).astype(np.float32)
+    noisy = rng.standard_normal(n).astype(np.float32)
+    special = smooth.copy()
+    special[::97] = 0.0
+    special[5::1013] = np.float32("nan")
+    special[7::511] = np.float32("-inf")
+    special[11::3] = special[10::3][: special[11::3].size]          # repeats: xor1 == 0 codes
+    for name, vals in (("smooth", smooth), ("noisy", noisy), ("special", special)):
+        for e1, e2 in ((4, 10), (2, 4)):
+            want = oracle.fpc_compress(vals.view(np.uint32), e1, e2)
+            got = ours.compress(vals, e1, e2)
+            assert got == want, (name, e1, e2, n, len(got), len(want))
+    assert np.array_equal(ours.decompress(got, 4), vals.view(np.uint32))

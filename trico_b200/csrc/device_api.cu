@@ -395,10 +395,48 @@ extern "C" int tb200_fpc_encode_v0(tb200_ctx* c, int wordsize, const void* d_in,
   if (wordsize != 4 && wordsize != 8) return fail_msg("tb200_fpc_encode_v0: bad wordsize");
   norm_exponents(&e1, &e2);
   if (e1 < 2 || e2 < 2) return fail_msg("tb200_fpc_encode_v0: exponents below 2 are not supported");
+  const size_t tw = ((size_t)1 << e1) + ((size_t)1 << e2);
+  // K3L: long float streams whose tables fit shared memory are encoded tile-parallel (same bytes)
+  static int tiled = -1;
+  if (tiled < 0) { const char* e = getenv("TB200_FPC_V0_TILED"); tiled = e ? atoi(e) : 1; }
+  if (tiled && wordsize == 4 && n >= 8u * FPC_V0_TILE && tw <= 4096)
+    {
+    FpcV0TileArgs t;
+    t.in = d_in; t.n = n; t.stride = stride; t.nstreams = nstreams; t.e1 = e1; t.e2 = e2;
+    t.out = d_out; t.out_stride = out_stride; t.nbytes = d_nbytes;
+    t.ntiles = (n + FPC_V0_TILE - 1) / FPC_V0_TILE;
+    const size_t total = (size_t)t.ntiles * nstreams;
+    const uint32_t mw = (uint32_t)((tw + 31) / 32);
+    t.rec_words = (uint32_t)((2 * tw + mw + 3) & ~(size_t)3);
+    // workspace: [ticket 256 B][desc total u64][state total u32][records]
+    const size_t off_desc = 256, off_state = off_desc + total * 8, off_rec = (off_state + total * 4 + 255) & ~(size_t)255;
+    uint8_t* g = nullptr;
+    if (!big_prepare(c, off_rec + total * t.rec_words * 4, &g)) return 0;
+    CK(cudaMemsetAsync(g, 0, off_rec, c->stream));
+    t.ticket = reinterpret_cast<uint32_t*>(g);
+    t.desc = reinterpret_cast<uint64_t*>(g + off_desc);
+    t.state = reinterpret_cast<uint32_t*>(g + off_state);
+    t.records = reinterpret_cast<uint32_t*>(g + off_rec);
+    const size_t tw_pad = (tw + 3) & ~(size_t)3, mw_pad = (mw + 3u) & ~3u;
+    const size_t per_warp = (2 * tw_pad + 2 * mw_pad) * 4 + fpc_v0_tile_out_bytes(4, 8, 3);
+    const size_t smem = per_warp * FPC_V0_WARPS;
+    if (!set_smem(fpc_encode_v0_tiles_kernel<uint32_t>, smem, c)) return 0;
+    int per_sm = 0, sms = 0;
+    if (!persistent_grid(fpc_encode_v0_tiles_kernel<uint32_t>, FPC_V0_WARPS * 32, smem, c, &per_sm, &sms)) return 0;
+    if (per_sm >= 1)
+      {
+      uint64_t grid = (uint64_t)per_sm * sms;                        // every CTA resident: the look-backs rely on it
+      const uint64_t want = (total + FPC_V0_WARPS - 1) / FPC_V0_WARPS;
+      if (grid > want) grid = want;
+      fpc_encode_v0_tiles_kernel<uint32_t><<<(unsigned)grid, FPC_V0_WARPS * 32, smem, c->stream>>>(t);
+      c->launches++;
+      CK(cudaGetLastError());
+      return 1;
+      }
+    }
   FpcLegacyEncodeArgs a;
   a.in = d_in; a.n = n; a.stride = stride; a.nstreams = nstreams; a.e1 = e1; a.e2 = e2;
   a.out = d_out; a.out_stride = out_stride; a.nbytes = d_nbytes; a.gtables = nullptr;
-  const size_t tw = ((size_t)1 << e1) + ((size_t)1 << e2);
   size_t smem = tw * wordsize;
   if (smem > 64 * 1024)
     {

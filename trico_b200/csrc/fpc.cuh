@@ -89,15 +89,22 @@ __device__ __forceinline__ void fpc_st8(uint8_t* gp, uint32_t sp, uint32_t off, 
 // values), so a lane's offset is HDR * (groups started so far) plus the residual bytes of the
 // lanes before it, and that sum is three (four) ballots of the bits of nb and population counts.
 // ---------------------------------------------------------------------------------------------
-template <typename W, bool OUT_SHARED, typename SrcPtr>
+// CONTINUE: the chain does not start here - the tables hold the predictor state in front of
+// src[0] and (v_before, ta_before, tb_before) are the previous value and the stride classes of
+// the two previous elements (the tile-parallel v0 encoder below).
+template <typename W, bool OUT_SHARED, typename SrcPtr, bool CONTINUE = false>
 __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride, uint32_t cnt,
-                                                    uint8_t* out, W* T1, W* T2, int e1, int e2)
+                                                    uint8_t* out, W* T1, W* T2, int e1, int e2,
+                                                    W v_before = 0, uint32_t ta_before = 0, uint32_t tb_before = 0)
   {
   using TR = FpcTraits<W>;
   const unsigned lane = lane_id();
   const unsigned lt = lanemask_lt(), gt = lanemask_gt();
-  for (uint32_t i = lane; i < (1u << e1); i += 32) T1[i] = 0;
-  for (uint32_t i = lane; i < (1u << e2); i += 32) T2[i] = 0;
+  if (!CONTINUE)
+    {
+    for (uint32_t i = lane; i < (1u << e1); i += 32) T1[i] = 0;
+    for (uint32_t i = lane; i < (1u << e2); i += 32) T2[i] = 0;
+    }
   __syncwarp();
 
   const int h = e2 >> 1;
@@ -106,8 +113,8 @@ __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride,
   const uint32_t out_s = OUT_SHARED ? (uint32_t)__cvta_generic_to_shared(out) : 0u;
   const uint32_t gl = lane & (TR::GROUP - 1);               // position inside the group
   const uint32_t hdr_before = TR::HDR * (lane / TR::GROUP + 1);   // code-word bytes up to and including this lane's group
-  W carry_v = 0;
-  uint32_t carry_ta = 0, carry_tb = 0;      // t[j-1], t[j-2] entering the window
+  W carry_v = CONTINUE ? v_before : (W)0;
+  uint32_t carry_ta = CONTINUE ? ta_before : 0u, carry_tb = CONTINUE ? tb_before : 0u;      // t[j-1], t[j-2] entering the window
   uint32_t obase = 0;
 
   for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
@@ -273,6 +280,195 @@ fpc_encode_legacy_kernel(const FpcLegacyEncodeArgs a)
   else
     nb = fpc_encode_warp<W, false>(src, a.stride, a.n, out + 5, T1, T2, a.e1, a.e2);
   if (lane == 0) a.nbytes[c] = nb + 5;
+  }
+
+// ---------------------------------------------------------------------------------------------
+// K3L: TILE-PARALLEL encoder of reference-format (v0) streams - byte-identical to trico_compress
+// (fpc.c:86-210), many warps on ONE chain.
+//
+// The chain of a v0 stream runs through the predictor tables, and both predictors are finite-context
+// (see DESIGN.md): the prediction for an element is the value (stride) that followed the MOST
+// RECENT EARLIER element with the same context.  Inside a tile of FPC_V0_TILE values
+// fpc_encode_warp finds that element itself; what a tile needs from the past is the table as it
+// stands in front of it - for every context the last writer among all earlier tiles.  "Last writer
+// wins" is associative, so that state is a scan over tiles:
+//   1. the warp computes its tile's LOCAL table (last writer per context inside the tile) and the
+//      mask of contexts it wrote, and publishes both;
+//   2. look-back: walking the earlier tiles of the stream it fills the contexts it has not seen yet
+//      from their local tables until it meets a tile whose INCLUSIVE table (the full state behind
+//      that tile) is published, which completes the state; it then publishes its own inclusive table;
+//   3. it encodes the tile with fpc_encode_warp, tables initialised to the state from 2. and the
+//      carries (previous value, stride classes of the two previous elements) read from the input;
+//   4. a second look-back over byte counts gives the tile's offset in the stream.
+// Tiles take their number from a ticket, so a tile only ever waits for tiles that have started.
+// Tables of (e1, e2) = (4, 10) floats: 1040 words; the kernel takes any table that fits shared
+// memory twice (the (20, 20) tables of v0 doubles do not: those streams keep the one-warp kernel).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t FPC_V0_TILE = 2048;
+constexpr int FPC_V0_WARPS = 4;
+
+struct FpcV0TileArgs
+  {
+  const void* in;          // device: component c, element j at in[(j * stride + c)]
+  uint32_t n;
+  uint32_t stride;
+  int nstreams;
+  int e1, e2;
+  uint8_t* out;            // nstreams slots of out_stride bytes: 5-byte header + groups
+  uint64_t out_stride;
+  uint32_t* nbytes;        // [nstreams]
+  uint32_t ntiles;         // per stream
+  uint32_t* ticket;        // zeroed
+  uint64_t* desc;          // [nstreams * ntiles], zeroed: byte-count look-back
+  uint32_t* state;         // [nstreams * ntiles], zeroed: 0 nothing, 1 local table, 2 inclusive table published
+  uint32_t* records;       // [nstreams * ntiles] records of rec_words words: local[tw] mask[mw] inclusive[tw]
+  uint32_t rec_words;
+  };
+
+__host__ __device__ constexpr uint32_t fpc_v0_tile_out_bytes(int wbytes, int group, int hdr)
+  { return ((FPC_V0_TILE / group) * hdr + FPC_V0_TILE * wbytes + 63u) & ~15u; }      // + what warp_copy_smem_to_global reads behind the last byte
+
+template <typename W>
+__global__ void __launch_bounds__(FPC_V0_WARPS * 32)
+fpc_encode_v0_tiles_kernel(const FpcV0TileArgs a)
+  {
+  using TR = FpcTraits<W>;
+  static_assert(sizeof(W) == 4, "records are 32-bit words");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  const unsigned gt = lanemask_gt();
+  const uint32_t nt1 = 1u << a.e1, nt2 = 1u << a.e2, tw = nt1 + nt2, mw = (tw + 31u) >> 5;
+  const uint32_t tw_pad = (tw + 3u) & ~3u, mw_pad = (mw + 3u) & ~3u;
+  constexpr uint32_t OUTB = fpc_v0_tile_out_bytes(TR::WBYTES, TR::GROUP, TR::HDR);
+  const size_t per_warp = (size_t)(2u * tw_pad + 2u * mw_pad) * 4u + OUTB;
+  uint8_t* my = smem_raw + (size_t)warp * per_warp;
+  W* T = reinterpret_cast<W*>(my);                         // state in front of the tile, then the encoder's working tables
+  W* LT = T + tw_pad;                                      // last writer per context inside the tile
+  uint32_t* M = reinterpret_cast<uint32_t*>(LT + tw_pad);  // contexts written inside the tile
+  uint32_t* AM = M + mw_pad;                               // contexts filled during the look-back
+  uint8_t* ob = reinterpret_cast<uint8_t*>(AM + mw_pad);
+  const uint32_t total_tiles = a.ntiles * (uint32_t)a.nstreams;
+  const int h = a.e2 >> 1;
+  const uint32_t lowmask = (1u << h) - 1u;
+
+  for (;;)
+    {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(a.ticket, 1u);
+    t = __shfl_sync(FULL, t, 0);
+    if (t >= total_tiles) break;
+    const uint32_t c = t % (uint32_t)a.nstreams, k = t / (uint32_t)a.nstreams;    // tile k of stream c: its predecessors hold lower tickets
+    const uint32_t j0 = k * FPC_V0_TILE;
+    const uint32_t cnt = a.n - j0 < FPC_V0_TILE ? a.n - j0 : FPC_V0_TILE;
+    const W* src = reinterpret_cast<const W*>(a.in) + c;
+    // the chain's registers in front of the tile (fpc.c:104-113: everything starts at zero)
+    const W pv1 = j0 >= 1u ? src[(size_t)(j0 - 1u) * a.stride] : (W)0;
+    const W pv2 = j0 >= 2u ? src[(size_t)(j0 - 2u) * a.stride] : (W)0;
+    const W pv3 = j0 >= 3u ? src[(size_t)(j0 - 3u) * a.stride] : (W)0;
+    const uint32_t ta0 = (uint32_t)((W)(pv1 - pv2) >> (TR::BITS - a.e2)), tb0 = (uint32_t)((W)(pv2 - pv3) >> (TR::BITS - a.e2));
+    const uint32_t idx = k * (uint32_t)a.nstreams + c;
+    uint32_t* rec = a.records + (size_t)idx * a.rec_words;
+
+    // ---- 1. local table ----
+    for (uint32_t i = lane; i < mw; i += 32) { M[i] = 0; AM[i] = 0; }
+    for (uint32_t i = lane; i < tw; i += 32) T[i] = 0;
+    __syncwarp();
+      {
+      W carry_v = pv1;
+      uint32_t carry_ta = ta0, carry_tb = tb0;
+      for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
+        {
+        const uint32_t j = i0 + lane;
+        const bool act = j < cnt;
+        const W v = act ? src[(size_t)(j0 + j) * a.stride] : (W)0;
+        W vprev = __shfl_up_sync(FULL, v, 1);
+        if (lane == 0) vprev = carry_v;
+        const uint32_t c1 = (uint32_t)(vprev >> (TR::BITS - a.e1));
+        const unsigned m1 = __match_any_sync(FULL, c1);
+        const W s = v - vprev;
+        const uint32_t tt = (uint32_t)(s >> (TR::BITS - a.e2));
+        uint32_t ta = __shfl_up_sync(FULL, tt, 1);
+        uint32_t tb = __shfl_up_sync(FULL, tt, 2);
+        if (lane == 0) { ta = carry_ta; tb = carry_tb; }
+        if (lane == 1) { tb = carry_ta; }
+        const uint32_t c2 = nt1 + (((tb & lowmask) << h) ^ ta);
+        const unsigned m2 = __match_any_sync(FULL, c2);
+        const unsigned actmask = __ballot_sync(FULL, act);
+        // the last active element of every context wins (what a serial pass leaves)
+        if (act && ((m1 & gt & actmask) == 0)) { LT[c1] = v; atomicOr(&M[c1 >> 5], 1u << (c1 & 31u)); }
+        if (act && ((m2 & gt & actmask) == 0)) { LT[c2] = s; atomicOr(&M[c2 >> 5], 1u << (c2 & 31u)); }
+        carry_v = __shfl_sync(FULL, v, 31);
+        carry_tb = __shfl_sync(FULL, tt, 30);
+        carry_ta = __shfl_sync(FULL, tt, 31);
+        __syncwarp();
+        }
+      }
+    // publish it
+    for (uint32_t q = lane; q < tw; q += 32) if ((M[q >> 5] >> (q & 31u)) & 1u) __stcg(rec + q, (uint32_t)LT[q]);
+    for (uint32_t i = lane; i < mw; i += 32) __stcg(rec + tw + i, M[i]);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0 && k != 0u) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.state + idx), "r"(1u) : "memory");
+
+    // ---- 2. the state in front of the tile ----
+    for (int64_t p = (int64_t)k - 1; p >= 0; --p)
+      {
+      const uint32_t pidx = (uint32_t)p * (uint32_t)a.nstreams + c;
+      uint32_t st = 0;
+      if (lane == 0)
+        for (;;)
+          {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(st) : "l"(a.state + pidx) : "memory");
+          if (st != 0u) break;
+          __nanosleep(40);
+          }
+      st = __shfl_sync(FULL, st, 0);
+      const uint32_t* prec = a.records + (size_t)pidx * a.rec_words;
+      if (st == 2u)
+        { // the full state behind tile p: whatever is still open comes from it
+        const uint32_t* inc = prec + tw + mw;
+        for (uint32_t q = lane; q < tw; q += 32) if (!((AM[q >> 5] >> (q & 31u)) & 1u)) T[q] = (W)__ldcg(inc + q);
+        break;
+        }
+      // tile p's own writes: the contexts not seen yet
+      for (uint32_t i = 0; i < mw; ++i)
+        {
+        const uint32_t q = 32u * i + lane;
+        const uint32_t pm = __ldcg(prec + tw + i), have = AM[i];
+        const bool take = q < tw && ((pm & ~have) >> lane) & 1u;
+        if (take) T[q] = (W)__ldcg(prec + q);
+        __syncwarp();
+        if (lane == 0) AM[i] = have | pm;
+        }
+      __syncwarp();
+      }
+    __syncwarp();
+    // the state behind this tile, for its successors
+      {
+      uint32_t* inc = rec + tw + mw;
+      for (uint32_t q = lane; q < tw; q += 32) __stcg(inc + q, (uint32_t)(((M[q >> 5] >> (q & 31u)) & 1u) ? LT[q] : T[q]));
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.state + idx), "r"(2u) : "memory");
+      }
+
+    // ---- 3. encode the tile ----
+    const uint32_t nb = fpc_encode_warp<W, true, const W*, true>(src + (size_t)j0 * a.stride, a.stride, cnt, ob, T, T + nt1, a.e1, a.e2, pv1, ta0, tb0);
+    __syncwarp();
+
+    // ---- 4. place it ----
+    const uint64_t excl = lookback_exclusive(a.desc + (size_t)c * a.ntiles, k, nb);
+    uint8_t* out = a.out + (size_t)c * a.out_stride;
+    if (k == 0u && lane == 0)
+      {
+      out[0] = (uint8_t)(((a.e1 >> 1) << 4) | (a.e2 >> 1));                 // fpc.c:120
+      out[1] = (uint8_t)(a.n >> 24); out[2] = (uint8_t)(a.n >> 16);          // fpc.c:123-126
+      out[3] = (uint8_t)(a.n >> 8);  out[4] = (uint8_t)a.n;
+      }
+    warp_copy_smem_to_global(out + 5 + excl, ob, nb);
+    if (k == a.ntiles - 1u && lane == 0) a.nbytes[c] = (uint32_t)(excl + nb + 5u);
+    __syncwarp();
+    }
   }
 
 // ---------------------------------------------------------------------------------------------
