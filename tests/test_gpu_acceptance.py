@@ -217,12 +217,15 @@ def test_ratio_per_stream_type_against_reference_whole_stream(dev, oracle):
 
 
 # ------------------------------------------------ reference-format streams, tile-parallel (K3L)
+@pytest.mark.parametrize("run", [0, 3, 8])
 @pytest.mark.parametrize("n", [8 * 2048, 8 * 2048 + 1, 16391, 100003, 1_000_000, 3_000_001])
-def test_v0_stream_tile_parallel_is_byte_identical(ours, oracle, n):
+def test_v0_stream_tile_parallel_is_byte_identical(ours, oracle, monkeypatch, n, run):
     """trico_compress on long float arrays runs the tile-parallel encoder (fpc_encode_v0_tiles_kernel):
     the bytes are those of the serial reference algorithm (oracle.fpc_compress = fpc.c:86-210, pinned
     against the compiled reference in test_oracle.py), for smooth, noisy and special-value data and
     for two exponent pairs"""
+    if run:
+        monkeypatch.setenv("TB200_FPC_V0_RUN", str(run))       # tiles per warp run (default: by stream length; 1 at these sizes)
     rng = np.random.default_rng(n)
     i = np.arange(n)
     smooth = (5 * np.sin(0.0037 * i) * np.cos(0.00021 * i) + 0.01 * rng.random(n)).astype(np.float32)

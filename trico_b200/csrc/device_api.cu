@@ -405,18 +405,8 @@ extern "C" int tb200_fpc_encode_v0(tb200_ctx* c, int wordsize, const void* d_in,
     t.in = d_in; t.n = n; t.stride = stride; t.nstreams = nstreams; t.e1 = e1; t.e2 = e2;
     t.out = d_out; t.out_stride = out_stride; t.nbytes = d_nbytes;
     t.ntiles = (n + FPC_V0_TILE - 1) / FPC_V0_TILE;
-    const size_t total = (size_t)t.ntiles * nstreams;
     const uint32_t mw = (uint32_t)((tw + 31) / 32);
     t.rec_words = (uint32_t)((2 * tw + mw + 3) & ~(size_t)3);
-    // workspace: [ticket 256 B][desc total u64][state total u32][records]
-    const size_t off_desc = 256, off_state = off_desc + total * 8, off_rec = (off_state + total * 4 + 255) & ~(size_t)255;
-    uint8_t* g = nullptr;
-    if (!big_prepare(c, off_rec + total * t.rec_words * 4, &g)) return 0;
-    CK(cudaMemsetAsync(g, 0, off_rec, c->stream));
-    t.ticket = reinterpret_cast<uint32_t*>(g);
-    t.desc = reinterpret_cast<uint64_t*>(g + off_desc);
-    t.state = reinterpret_cast<uint32_t*>(g + off_state);
-    t.records = reinterpret_cast<uint32_t*>(g + off_rec);
     const size_t tw_pad = (tw + 3) & ~(size_t)3, mw_pad = (mw + 3u) & ~3u;
     const size_t per_warp = (2 * tw_pad + 2 * mw_pad) * 4 + fpc_v0_tile_out_bytes(4, 8, 3);
     const size_t smem = per_warp * FPC_V0_WARPS;
@@ -426,8 +416,29 @@ extern "C" int tb200_fpc_encode_v0(tb200_ctx* c, int wordsize, const void* d_in,
     if (per_sm >= 1)
       {
       uint64_t grid = (uint64_t)per_sm * sms;                        // every CTA resident: the look-backs rely on it
-      const uint64_t want = (total + FPC_V0_WARPS - 1) / FPC_V0_WARPS;
+      // tiles per run: up to 8, as long as every warp of the grid still gets about four runs
+      const uint64_t warps = grid * FPC_V0_WARPS;
+      uint64_t run = ((uint64_t)t.ntiles * nstreams) / (4 * warps);
+      if (run < 1) run = 1;
+      if (run > 8) run = 8;
+      if (const char* e = getenv("TB200_FPC_V0_RUN")) { const int v = atoi(e); if (v >= 1 && v <= 64) run = v; }
+      t.run = (uint32_t)run;
+      t.nruns = (uint32_t)((t.ntiles + run - 1) / run);
+      const size_t total = (size_t)t.ntiles * nstreams, total_runs = (size_t)t.nruns * nstreams;
+      // workspace: [ticket 256 B][desc: u64 per tile][state: u32 per run][records per run]
+      const size_t off_desc = 256, off_state = off_desc + total * 8, off_rec = (off_state + total_runs * 4 + 255) & ~(size_t)255;
+      const uint64_t want = (total_runs + FPC_V0_WARPS - 1) / FPC_V0_WARPS;
       if (grid > want) grid = want;
+      t.slot = fpc_v0_tile_out_bytes(4, 8, 3);
+      const size_t off_scr = (off_rec + total_runs * t.rec_words * 4 + 255) & ~(size_t)255;
+      uint8_t* g = nullptr;
+      if (!big_prepare(c, off_scr + (size_t)grid * FPC_V0_WARPS * run * t.slot, &g)) return 0;
+      CK(cudaMemsetAsync(g, 0, off_rec, c->stream));
+      t.scratch = g + off_scr;
+      t.ticket = reinterpret_cast<uint32_t*>(g);
+      t.desc = reinterpret_cast<uint64_t*>(g + off_desc);
+      t.state = reinterpret_cast<uint32_t*>(g + off_state);
+      t.records = reinterpret_cast<uint32_t*>(g + off_rec);
       fpc_encode_v0_tiles_kernel<uint32_t><<<(unsigned)grid, FPC_V0_WARPS * 32, smem, c->stream>>>(t);
       c->launches++;
       CK(cudaGetLastError());

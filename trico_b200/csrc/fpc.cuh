@@ -117,12 +117,14 @@ __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride,
   uint32_t carry_ta = CONTINUE ? ta_before : 0u, carry_tb = CONTINUE ? tb_before : 0u;      // t[j-1], t[j-2] entering the window
   uint32_t obase = 0;
 
+  W vnext = lane < cnt ? (W)src[(size_t)lane * stride] : (W)0;      // loads run one window ahead
   for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
     {
     const uint32_t j = i0 + lane;
     const bool full = i0 + 32 <= cnt;       // warp-uniform: every lane holds a value
     const bool act = full || j < cnt;
-    const W v = act ? (W)src[(size_t)j * stride] : (W)0;
+    const W v = vnext;
+    vnext = j + 32u < cnt ? (W)src[(size_t)(j + 32u) * stride] : (W)0;
     W vprev = __shfl_up_sync(FULL, v, 1);
     if (lane == 0) vprev = carry_v;
 
@@ -292,18 +294,25 @@ fpc_encode_legacy_kernel(const FpcLegacyEncodeArgs a)
 // fpc_encode_warp finds that element itself; what a tile needs from the past is the table as it
 // stands in front of it - for every context the last writer among all earlier tiles.  "Last writer
 // wins" is associative, so that state is a scan over tiles:
-//   1. the warp computes its tile's LOCAL table (last writer per context inside the tile) and the
-//      mask of contexts it wrote, and publishes both;
-//   2. look-back: walking the earlier tiles of the stream it fills the contexts it has not seen yet
-//      from their local tables until it meets a tile whose INCLUSIVE table (the full state behind
-//      that tile) is published, which completes the state; it then publishes its own inclusive table;
-//   3. it encodes the tile with fpc_encode_warp, tables initialised to the state from 2. and the
-//      carries (previous value, stride classes of the two previous elements) read from the input;
-//   4. a second look-back over byte counts gives the tile's offset in the stream.
-// Tiles take their number from a ticket, so a tile only ever waits for tiles that have started.
+// A warp takes a RUN of consecutive tiles (the unit of the table scan; 1..8 tiles, as many as still
+// leave every warp of the grid a few runs):
+//   1. it computes the run's LOCAL table (last writer per context inside the run) and the mask of
+//      contexts it wrote, and publishes both;
+//   2. look-back: walking the earlier runs of the stream it fills the contexts it has not seen yet
+//      from their local tables until it meets a run whose INCLUSIVE table (the full state behind
+//      that run) is published, which completes the state; it then publishes its own inclusive table;
+//   3. it encodes its tiles one after the other with fpc_encode_warp - tables initialised to the
+//      state from 2. and simply carried from tile to tile, the chain's registers (previous value,
+//      stride classes of the two previous elements) read from the input;
+//   4. per tile, a second look-back over byte counts gives the offset in the stream.
+// Runs take their number from a ticket, so a run only ever waits for runs that have started.
+// (With one tile per run a tile visited ~25 predecessors on average, 4.3 KB each: the scan, not the
+// encoder, set the speed.)
 // Tables of (e1, e2) = (4, 10) floats: 1040 words; the kernel takes any table that fits shared
 // memory twice (the (20, 20) tables of v0 doubles do not: those streams keep the one-warp kernel).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy_global(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n);      // below
+
 constexpr uint32_t FPC_V0_TILE = 2048;
 constexpr int FPC_V0_WARPS = 4;
 
@@ -318,11 +327,15 @@ struct FpcV0TileArgs
   uint64_t out_stride;
   uint32_t* nbytes;        // [nstreams]
   uint32_t ntiles;         // per stream
+  uint32_t run;            // tiles per run: a warp takes a run of consecutive tiles, the table scan links runs
+  uint32_t nruns;          // per stream
   uint32_t* ticket;        // zeroed
-  uint64_t* desc;          // [nstreams * ntiles], zeroed: byte-count look-back
-  uint32_t* state;         // [nstreams * ntiles], zeroed: 0 nothing, 1 local table, 2 inclusive table published
-  uint32_t* records;       // [nstreams * ntiles] records of rec_words words: local[tw] mask[mw] inclusive[tw]
+  uint64_t* desc;          // [nstreams * ntiles], zeroed: byte-count look-back (per tile)
+  uint32_t* state;         // [nstreams * nruns], zeroed: 0 nothing, 1 local table, 2 inclusive table published
+  uint32_t* records;       // [nstreams * nruns] records of rec_words words: local[tw] mask[mw] inclusive[tw]
   uint32_t rec_words;
+  uint8_t* scratch;        // [warps of the grid][run] slots of `slot` bytes: a run's tiles until its offset is known
+  uint32_t slot;
   };
 
 __host__ __device__ constexpr uint32_t fpc_v0_tile_out_bytes(int wbytes, int group, int hdr)
@@ -347,7 +360,7 @@ fpc_encode_v0_tiles_kernel(const FpcV0TileArgs a)
   uint32_t* M = reinterpret_cast<uint32_t*>(LT + tw_pad);  // contexts written inside the tile
   uint32_t* AM = M + mw_pad;                               // contexts filled during the look-back
   uint8_t* ob = reinterpret_cast<uint8_t*>(AM + mw_pad);
-  const uint32_t total_tiles = a.ntiles * (uint32_t)a.nstreams;
+  const uint32_t total_tiles = a.nruns * (uint32_t)a.nstreams;       // tickets: runs
   const int h = a.e2 >> 1;
   const uint32_t lowmask = (1u << h) - 1u;
 
@@ -357,11 +370,11 @@ fpc_encode_v0_tiles_kernel(const FpcV0TileArgs a)
     if (lane == 0) t = atomicAdd(a.ticket, 1u);
     t = __shfl_sync(FULL, t, 0);
     if (t >= total_tiles) break;
-    const uint32_t c = t % (uint32_t)a.nstreams, k = t / (uint32_t)a.nstreams;    // tile k of stream c: its predecessors hold lower tickets
-    const uint32_t j0 = k * FPC_V0_TILE;
-    const uint32_t cnt = a.n - j0 < FPC_V0_TILE ? a.n - j0 : FPC_V0_TILE;
+    const uint32_t c = t % (uint32_t)a.nstreams, k = t / (uint32_t)a.nstreams;    // run k of stream c: its predecessors hold lower tickets
+    const uint32_t j0 = k * a.run * FPC_V0_TILE;
+    const uint32_t cnt = a.n - j0 < a.run * FPC_V0_TILE ? a.n - j0 : a.run * FPC_V0_TILE;
     const W* src = reinterpret_cast<const W*>(a.in) + c;
-    // the chain's registers in front of the tile (fpc.c:104-113: everything starts at zero)
+    // the chain's registers in front of the run (fpc.c:104-113: everything starts at zero)
     const W pv1 = j0 >= 1u ? src[(size_t)(j0 - 1u) * a.stride] : (W)0;
     const W pv2 = j0 >= 2u ? src[(size_t)(j0 - 2u) * a.stride] : (W)0;
     const W pv3 = j0 >= 3u ? src[(size_t)(j0 - 3u) * a.stride] : (W)0;
@@ -376,11 +389,13 @@ fpc_encode_v0_tiles_kernel(const FpcV0TileArgs a)
       {
       W carry_v = pv1;
       uint32_t carry_ta = ta0, carry_tb = tb0;
+      W vnext = lane < cnt ? src[(size_t)(j0 + lane) * a.stride] : (W)0;       // one window ahead: the loads are strided and far
       for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
         {
         const uint32_t j = i0 + lane;
         const bool act = j < cnt;
-        const W v = act ? src[(size_t)(j0 + j) * a.stride] : (W)0;
+        const W v = vnext;
+        vnext = j + 32u < cnt ? src[(size_t)(j0 + j + 32u) * a.stride] : (W)0;
         W vprev = __shfl_up_sync(FULL, v, 1);
         if (lane == 0) vprev = carry_v;
         const uint32_t c1 = (uint32_t)(vprev >> (TR::BITS - a.e1));
@@ -430,16 +445,24 @@ fpc_encode_v0_tiles_kernel(const FpcV0TileArgs a)
         for (uint32_t q = lane; q < tw; q += 32) if (!((AM[q >> 5] >> (q & 31u)) & 1u)) T[q] = (W)__ldcg(inc + q);
         break;
         }
-      // tile p's own writes: the contexts not seen yet
+      // tile p's own writes: the contexts not seen yet.  Lane i owns mask word i (tables of up to
+      // 1056 entries: 33 words, the last one handled by every lane alike), so the words arrive in one
+      // round trip and the value loads below do not wait for one another.
+      const uint32_t have_l = lane < mw ? AM[lane] : 0u, pm_l = lane < mw ? __ldcg(prec + tw + lane) : 0u;
+      uint32_t have_x = 0, pm_x = 0;
+      if (mw > 32u) { have_x = AM[32]; pm_x = __ldcg(prec + tw + 32u); }
+      const uint32_t new_l = pm_l & ~have_l, new_x = pm_x & ~have_x;
+#pragma unroll 4
       for (uint32_t i = 0; i < mw; ++i)
         {
+        const uint32_t nw = i < 32u ? __shfl_sync(FULL, new_l, (int)i) : new_x;
+        if (nw == 0u) continue;
         const uint32_t q = 32u * i + lane;
-        const uint32_t pm = __ldcg(prec + tw + i), have = AM[i];
-        const bool take = q < tw && ((pm & ~have) >> lane) & 1u;
-        if (take) T[q] = (W)__ldcg(prec + q);
-        __syncwarp();
-        if (lane == 0) AM[i] = have | pm;
+        if ((nw >> lane) & 1u) T[q] = (W)__ldcg(prec + q);
         }
+      __syncwarp();
+      if (lane < mw) AM[lane] = have_l | pm_l;
+      if (mw > 32u && lane == 0) AM[32] = have_x | pm_x;
       __syncwarp();
       }
     __syncwarp();
@@ -452,21 +475,47 @@ fpc_encode_v0_tiles_kernel(const FpcV0TileArgs a)
       if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.state + idx), "r"(2u) : "memory");
       }
 
-    // ---- 3. encode the tile ----
-    const uint32_t nb = fpc_encode_warp<W, true, const W*, true>(src + (size_t)j0 * a.stride, a.stride, cnt, ob, T, T + nt1, a.e1, a.e2, pv1, ta0, tb0);
-    __syncwarp();
-
-    // ---- 4. place it ----
-    const uint64_t excl = lookback_exclusive(a.desc + (size_t)c * a.ntiles, k, nb);
+    // ---- 3. encode the run's tiles: bytes to the warp's scratch slots, byte counts published at once ----
+    // (Placing every tile as soon as it is encoded would chain the runs: the first tile of a run would
+    // wait for the LAST tile of the run before it.  The counts of a run are all out when its encoding
+    // ends, which is about when its successor's ends.)
     uint8_t* out = a.out + (size_t)c * a.out_stride;
-    if (k == 0u && lane == 0)
+    uint8_t* scr = a.scratch + (size_t)(blockIdx.x * FPC_V0_WARPS + warp) * a.run * a.slot;
+    uint64_t* desc = a.desc + (size_t)c * a.ntiles;
+    const uint32_t tile0 = k * a.run;
+    uint32_t nb0 = 0;
+    for (uint32_t i0 = 0, i = 0; i0 < cnt; i0 += FPC_V0_TILE, ++i)
+      {
+      const uint32_t jt = j0 + i0;
+      const uint32_t tc = cnt - i0 < FPC_V0_TILE ? cnt - i0 : FPC_V0_TILE;
+      const W q1 = jt >= 1u ? src[(size_t)(jt - 1u) * a.stride] : (W)0;
+      const W q2 = jt >= 2u ? src[(size_t)(jt - 2u) * a.stride] : (W)0;
+      const W q3 = jt >= 3u ? src[(size_t)(jt - 3u) * a.stride] : (W)0;
+      const uint32_t nb = fpc_encode_warp<W, true, const W*, true>(src + (size_t)jt * a.stride, a.stride, tc, ob, T, T + nt1, a.e1, a.e2, q1,
+                                                                   (uint32_t)((W)(q1 - q2) >> (TR::BITS - a.e2)), (uint32_t)((W)(q2 - q3) >> (TR::BITS - a.e2)));
+      __syncwarp();
+      lookback_publish(desc, tile0 + i, nb);
+      if (i == 0u) nb0 = nb;
+      uint4* sv = reinterpret_cast<uint4*>(scr + (size_t)i * a.slot);
+      for (uint32_t v4 = lane; v4 < (nb + 15u) >> 4; v4 += 32) __stcg(sv + v4, *reinterpret_cast<const uint4*>(ob + 16u * v4));
+      __syncwarp();
+      }
+    // ---- 4. the run's offset, then its tiles to their places ----
+    uint64_t at = lookback_walk(desc, tile0, nb0);
+    if (tile0 == 0u && lane == 0)
       {
       out[0] = (uint8_t)(((a.e1 >> 1) << 4) | (a.e2 >> 1));                 // fpc.c:120
       out[1] = (uint8_t)(a.n >> 24); out[2] = (uint8_t)(a.n >> 16);          // fpc.c:123-126
       out[3] = (uint8_t)(a.n >> 8);  out[4] = (uint8_t)a.n;
       }
-    warp_copy_smem_to_global(out + 5 + excl, ob, nb);
-    if (k == a.ntiles - 1u && lane == 0) a.nbytes[c] = (uint32_t)(excl + nb + 5u);
+    for (uint32_t i0 = 0, i = 0; i0 < cnt; i0 += FPC_V0_TILE, ++i)
+      {
+      const uint32_t nb = i == 0u ? nb0 : (uint32_t)(lb_load(desc + tile0 + i) & LB_VAL);     // this warp published it
+      if (i != 0u && lane == 0) lb_store(desc + tile0 + i, LB_INC | (at + nb));               // successors stop here
+      warp_copy_global(out + 5 + at, scr + (size_t)i * a.slot, nb);
+      at += nb;
+      }
+    if (tile0 + (cnt + FPC_V0_TILE - 1u) / FPC_V0_TILE == a.ntiles && lane == 0) a.nbytes[c] = (uint32_t)(at + 5u);
     __syncwarp();
     }
   }
