@@ -94,6 +94,11 @@ TB200_API int tb200_lz4_decode_async(tb200_ctx* ctx, int wordsize, const uint8_t
                      uint64_t payload_bytes, uint64_t n, int log2_chunk, void* d_out, uint32_t* d_status);
 /* reference-format (v0) planes: `nplanes` whole-plane LZ4 blocks at d_base + offsets[p] of
  * nbytes[p] compressed bytes, each decoding to n bytes; merged into n elements of nplanes bytes. */
+/* reference-format planes from the GPU: plane p of the n wordsize-byte elements as ONE LZ4 block
+ * (what LZ4_compress_default over the plane is to the reference's writers, trico.c:346) at
+ * d_out + p * out_stride, its size in d_nbytes[p]; out_stride >= tb200_lz4_v0_bound(n) */
+TB200_API uint64_t tb200_lz4_v0_bound(uint64_t n);
+TB200_API int tb200_lz4_encode_v0(tb200_ctx* ctx, int wordsize, const void* d_in, uint64_t n, uint8_t* d_out, uint64_t out_stride, uint64_t* d_nbytes);
 TB200_API int tb200_lz4_decode_v0(tb200_ctx* ctx, int nplanes, const uint8_t* d_base, const uint64_t* offsets,
                         const uint32_t* nbytes, uint64_t n, void* d_out);
 

@@ -241,3 +241,34 @@ def test_v0_stream_tile_parallel_is_byte_identical(ours, oracle, monkeypatch, n,
             got = ours.compress(vals, e1, e2)
             assert got == want, (name, e1, e2, n, len(got), len(want))
     assert np.array_equal(ours.decompress(got, 4), vals.view(np.uint32))
+
+
+# ------------------------------------------------ reference-format LZ4 planes from the GPU
+def _v0_plane_cases():
+    rng = np.random.default_rng(21)
+    from trico_b200.synth import grid_mesh
+    _, t = grid_mesh(700, 600, jitter=1.0, seed=9)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bunny_full.npz"))
+    n = 300_007
+    yield "grid triangles u32", t.reshape(-1).astype(np.uint32)
+    yield "bunny triangles u32", z["triangles"].astype(np.uint32).reshape(-1)
+    yield "noise u32 (all literals)", rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    yield "constant u16", np.full(n, 0x1234, np.uint16)
+    yield "u8 runs", np.repeat(rng.integers(0, 5, n // 7 + 1), 7)[:n].astype(np.uint8)
+    yield "u64 ids", (np.arange(n, dtype=np.uint64) // 3) | (np.uint64(5) << np.uint64(40))
+    yield "mixed u32: noise, then constant, then noise", np.concatenate([rng.integers(0, 2 ** 32, 40_000, dtype=np.uint64), np.full(50_000, 7, np.uint64), rng.integers(0, 2 ** 32, 33_333, dtype=np.uint64)]).astype(np.uint32)
+    for m in (1, 12, 13, 100, 16384, 16385, 32768 + 5):
+        yield f"short u32 ({m})", (np.arange(m) // 2).astype(np.uint32)
+
+
+def test_v0_lz4_planes_are_single_valid_blocks(dev, oracle):
+    """tb200_lz4_encode_v0: every byte plane is ONE LZ4 block that satisfies the encoder rules
+    (oracle.lz4_validate: lz4.c:189-196) and decodes to the plane with the CPU decoder"""
+    for name, data in _v0_plane_cases():
+        planes = oracle.planes_split(data)
+        blocks = dev.lz4_encode_v0(data)
+        assert len(blocks) == data.dtype.itemsize
+        for p, blk in enumerate(blocks):
+            raw = planes[p].tobytes()
+            assert oracle.lz4_validate(blk, len(raw)) >= 0, (name, p)
+            assert oracle.lz4_decompress(blk, len(raw)) == raw, (name, p)

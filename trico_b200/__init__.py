@@ -60,6 +60,8 @@ def load() -> C.CDLL:
         "tb200_lz4_encode": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp, _vp]),
         "tb200_lz4_decode": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_uint64, C.c_uint64, C.c_int, _vp]),
         "tb200_lz4_decode_v0": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint64, _vp]),
+        "tb200_lz4_v0_bound": (C.c_uint64, [C.c_uint64]),
+        "tb200_lz4_encode_v0": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _vp, C.c_uint64, _vp]),
         "tb200_encode_stream": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, C.c_int, _vp, C.c_uint64, _vp]),
         "tb200_decode_stream": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
         "tb200_deinterleave": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_uint64, _vp]),
@@ -180,6 +182,17 @@ class Device:
     def decode_stream_device(self, header: bytes, d_stream: int, stream_bytes: int, d_out: int):
         hb = (C.c_uint8 * 15).from_buffer_copy(header[:15])
         self._ck(self.lib.tb200_decode_stream(self.ctx, hb, _vp(d_stream), stream_bytes, _vp(d_out)))
+
+    def lz4_encode_v0(self, data) -> list:
+        """host array of 1/2/4/8-byte integers -> one reference-format LZ4 block per byte plane (LSB first)"""
+        data = np.ascontiguousarray(data).reshape(-1)
+        w, n = data.dtype.itemsize, data.size
+        stride = (self.lib.tb200_lz4_v0_bound(n) + 255) & ~255
+        d_in, d_out, d_nb = self.upload(data), self.alloc(stride * w), self.alloc(64)
+        self._ck(self.lib.tb200_lz4_encode_v0(self.ctx, w, _vp(d_in.ptr), n, _vp(d_out.ptr), stride, _vp(d_nb.ptr)))
+        self.sync()
+        nb = self.download(d_nb.ptr, 8 * w).view(np.uint64)
+        return [self.download(d_out.ptr + p * stride, int(nb[p])).tobytes() for p in range(w)]
 
     def encode_stream(self, stream_type: int, data, count: int, log2_chunk: int = 0) -> bytes:
         """host array -> v1 stream bytes (type byte first)."""

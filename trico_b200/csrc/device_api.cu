@@ -7,6 +7,7 @@
 #include "lz4.cuh"
 #include "lz4_lanes.cuh"
 #include "lz4_multi.cuh"
+#include "lz4_v0.cuh"
 #include "planes.cuh"
 
 #include <stdio.h>
