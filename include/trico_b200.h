@@ -157,6 +157,10 @@ TRICO_API const char* trico_b200_last_error(void);
 TRICO_API int trico_b200_set_chunking(void* archive, int fpc_log2_values, int lz4_log2_bytes);
 /* kernels launched on behalf of this archive so far */
 TRICO_API uint64_t trico_b200_launch_count(void* archive);
+/* 0: write this archive in the reference's own format (readable by an unmodified reference decoder),
+ * 1: the chunked container (default; TRICO_B200_FORMAT=0 changes the default for unmodified callers).
+ * Must be called before the first trico_write_*. */
+TRICO_API int trico_b200_set_format(void* archive, int version);
 
 #if defined(__cplusplus)
 }

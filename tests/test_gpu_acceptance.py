@@ -272,3 +272,78 @@ def test_v0_lz4_planes_are_single_valid_blocks(dev, oracle):
             raw = planes[p].tobytes()
             assert oracle.lz4_validate(blk, len(raw)) >= 0, (name, p)
             assert oracle.lz4_decompress(blk, len(raw)) == raw, (name, p)
+
+
+# ------------------------------------------------ whole archives in the reference's own format
+FPC_TYPES = [1, 2, 5, 6, 7, 8, 9, 10, 11, 12, 15, 16]
+
+
+def _golden_stream(golden, ty):
+    b = golden["bunny"]
+    if ty in (6, 8):
+        return b["in_6"].reshape(-1), int(b["cnt_6"])
+    return b[f"in_{ty}"].reshape(-1), int(b[f"cnt_{ty}"]) * (3 if ty == 7 else 1)
+
+
+def test_v0_archives_written_on_the_gpu(ours, oracle, golden, monkeypatch):
+    """TRICO_B200_FORMAT=0 (or trico_b200_set_format(archive, 0)): trico_write_* emit the reference's own
+    format - version 0, one FPC stream per component, one LZ4 block per byte plane - so an UNMODIFIED
+    reference decoder reads what the GPU wrote.  FPC streams are byte-identical to the reference's."""
+    from checkers import TricoCApi, REF_SO, have_ref
+    monkeypatch.setenv("TRICO_B200_FORMAT", "0")
+    streams = []
+    for ty in range(1, 21):
+        data, cnt = _golden_stream(golden, ty)
+        streams.append((ty, data, cnt // 3 if ty == 7 else cnt))
+    blob = ours.encode(streams)
+    assert blob[:4] == b"Trco" and int.from_bytes(blob[4:8], "little") == 0
+    # the CPU oracle's v0 reader (trico.c:943-1668 restated) decodes it
+    version, dec = oracle.read_archive(blob)
+    assert version == 0 and [d[0] for d in dec] == list(range(1, 21))
+    for ty, cnt, arr in dec:
+        assert arr.tobytes() == _golden_stream(golden, ty)[0].tobytes(), ty
+    # stream by stream: FPC streams equal the reference-format writer's bytes
+    off = 8
+    for ty in range(1, 21):
+        data, cnt = _golden_stream(golden, ty)
+        _, _, _, used = oracle.v0_read_stream(blob, off)
+        if ty in FPC_TYPES:
+            assert blob[off:off + used] == oracle.v0_write_stream(ty, data, cnt), ty
+        off += used
+    assert off == len(blob)
+    # our own reader (legacy kernels)
+    version, dec2 = ours.decode(blob, oracle)
+    assert version == 0
+    for ty, cnt, arr in dec2:
+        want, wcnt = _golden_stream(golden, ty)
+        assert cnt == wcnt and arr.tobytes() == want.tobytes(), ty
+    # the compiled, unmodified reference library (its u8 attribute reader is broken: trico.c:1439)
+    if have_ref():
+        ref = TricoCApi(REF_SO)
+        keep = [s for s in streams if s[0] != 17]
+        blob2 = ours.encode(keep)
+        version, dec3 = ref.decode(blob2, oracle)
+        assert version == 0 and [d[0] for d in dec3] == [s[0] for s in keep]
+        for ty, cnt, arr in dec3:
+            assert arr.tobytes() == _golden_stream(golden, ty)[0].tobytes(), ty
+
+
+def test_v0_archive_of_a_large_mesh(ours, oracle, monkeypatch):
+    """2 M vertices / 4 M triangles in the reference's format: the tile-parallel FPC encoder and the
+    merged LZ4 planes at a size where every path (runs of tiles, literal regions across blocks) is used"""
+    from checkers import TricoCApi, REF_SO, have_ref
+    from trico_b200.synth import grid_mesh
+    monkeypatch.setenv("TRICO_B200_FORMAT", "0")
+    v, t = grid_mesh(1500, 1400, jitter=1.0, seed=7)
+    nv, nt = v.shape[0], t.shape[0]
+    blob = ours.encode([(1, v.reshape(-1), nv), (3, t.reshape(-1), nt)], initial=1 << 20)
+    assert int.from_bytes(blob[4:8], "little") == 0
+    _, _, _, used = oracle.v0_read_stream(blob, 8)
+    assert blob[8:8 + used] == oracle.v0_write_stream(1, v.reshape(-1), nv)          # vertices: the reference's bytes
+    version, dec = oracle.read_archive(blob)
+    assert version == 0 and dec[0][2].tobytes() == v.tobytes() and dec[1][2].tobytes() == t.tobytes()
+    if have_ref():
+        version, dec = TricoCApi(REF_SO).decode(blob, oracle)
+        assert version == 0 and dec[0][2].tobytes() == v.tobytes() and dec[1][2].tobytes() == t.tobytes()
+    ref_size = 8 + len(oracle.v0_write_stream(1, v.reshape(-1), nv)) + len(oracle.v0_write_stream(3, t.reshape(-1), nt))
+    assert len(blob) <= ref_size * 1.05, (len(blob), ref_size)

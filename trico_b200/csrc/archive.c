@@ -214,6 +214,7 @@ typedef struct
   int data_on_device;
   int next_type;
   int fpc_log2, lz4_log2;                /* 0 = default */
+  int format;                            /* writer: 1 = chunked container (default), 0 = the reference's own format */
   worker* w;
   } archive;
 
@@ -264,6 +265,8 @@ void* trico_open_archive_for_writing(uint64_t initial_buffer_size)
   put32(a->buffer, TRICO_MAGIC);         /* trico.c:90-98 */
   put32(a->buffer + 4, 0);               /* version 0 until a chunked stream is appended */
   a->size = 8;
+  const char* fmt = getenv("TRICO_B200_FORMAT");   /* lets UNMODIFIED callers (trico_encoder) write reference-readable archives */
+  a->format = (fmt && fmt[0] == '0') ? 0 : 1;
   return a;
   }
 
@@ -306,6 +309,19 @@ int trico_b200_set_chunking(void* h, int fpc_log2_values, int lz4_log2_bytes)
   if (fpc_log2_values && (fpc_log2_values < 5 || fpc_log2_values > 12)) return 0;
   if (lz4_log2_bytes && (lz4_log2_bytes < 8 || lz4_log2_bytes > 15)) return 0;
   a->fpc_log2 = fpc_log2_values; a->lz4_log2 = lz4_log2_bytes;
+  return 1;
+  }
+
+/* 0: every stream of this archive is written in the reference's own layout (one FPC stream per
+ * component with (4,10) / (20,20) tables, one LZ4 block per byte plane: trico.c:215-262, :323-378), so
+ * an unmodified reference decoder reads it; 1 (default): the chunked container.  Must be chosen
+ * before the first stream is written. */
+int trico_b200_set_format(void* h, int version)
+  {
+  archive* a = (archive*)h;
+  if (!a || !a->writable || (version != 0 && version != 1)) return 0;
+  if (a->size > 8 && version != a->format) return 0;
+  a->format = version;
   return 1;
   }
 
@@ -575,6 +591,78 @@ static int read_stream_pipelined(archive* a, uint64_t start, const uint8_t* head
  * writer: one routine for all stream types (trico.c:215-858).  `count` is the value stored in
  * the stream header.
  * ------------------------------------------------------------------------------------------ */
+/* Reference-format stream (trico.c:215-262 float/double components, :323-378 byte planes):
+ *   u8 type, u32 count, then per component / plane: u32 nbytes + payload.
+ * FPC components come from the tile-parallel v0 encoder (byte-identical to trico_compress), the
+ * planes from tb200_lz4_encode_v0 (one valid LZ4 block per plane). */
+static int write_stream_v0(archive* a, int type, const void* data, uint32_t count, int codec, int ws, int nc, int pc)
+  {
+  worker* w = a->w;
+  const uint64_t n = (uint64_t)count * pc;                    /* values per component / bytes per plane */
+  const int nsub = codec == 1 ? nc : ws;
+  const uint64_t raw_bytes = n * ws * (codec == 1 ? nc : 1);
+  if (n > 0x7E000000ull) { set_err("stream too long for the reference format"); return 0; }
+  if (!buffer_reserve(a, 5)) return 0;
+  a->buffer[a->size] = (uint8_t)type;
+  put32(a->buffer + a->size + 1, count);
+  a->size += 5;
+  if (n == 0)
+    { /* what the reference's codecs leave of an empty input: an FPC header + one group of pad slots
+         (fpc.c:196-204), an LZ4 block that is one zero token */
+    for (int s = 0; s < nsub; ++s)
+      {
+      if (codec == 1)
+        {
+        uint32_t nb = 0; uint8_t* p = NULL;
+        if (ws == 4) trico_compress(&nb, &p, NULL, 0, 4, 10); else trico_compress_double_precision(&nb, &p, NULL, 0, 20, 20);
+        if (!p || !buffer_reserve(a, 4 + (uint64_t)nb)) { free(p); return 0; }
+        put32(a->buffer + a->size, nb); memcpy(a->buffer + a->size + 4, p, nb); a->size += 4 + (uint64_t)nb;
+        free(p);
+        }
+      else
+        {
+        if (!buffer_reserve(a, 5)) return 0;
+        put32(a->buffer + a->size, 1); a->buffer[a->size + 4] = 0; a->size += 5;
+        }
+      }
+    return 1;
+    }
+  const void* d_in = data;
+  if (!tb200_pointer_is_device(data))
+    {
+    if (!ensure(&w->d_raw, &w->raw_cap, raw_bytes + 64, w)) return 0;
+    if (!tb200_memcpy_h2d(w->ctx, w->d_raw, data, raw_bytes)) { set_dev_err(); return 0; }
+    d_in = w->d_raw;
+    }
+  const uint64_t per = ((codec == 1 ? tb200_fpc_v0_bound(ws, (uint32_t)n) : tb200_lz4_v0_bound(n)) + 255) & ~(uint64_t)255;
+  if (!ensure(&w->d_enc, &w->enc_cap, 256 + per * nsub, w)) return 0;
+  uint8_t* d_sizes = w->d_enc;                                /* u32 (FPC) / u64 (LZ4) per sub-stream */
+  uint8_t* d_pay = w->d_enc + 256;
+  int ok;
+  if (codec == 1) ok = tb200_fpc_encode_v0(w->ctx, ws, d_in, (uint32_t)n, (uint32_t)nc, nc, ws == 4 ? 4 : 20, ws == 4 ? 10 : 20, d_pay, per, (uint32_t*)d_sizes);
+  else            ok = tb200_lz4_encode_v0(w->ctx, ws, d_in, n, d_pay, per, (uint64_t*)d_sizes);
+  if (!ok) { set_dev_err(); return 0; }
+  uint64_t sizes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (!tb200_memcpy_d2h(w->ctx, sizes, d_sizes, 64) || !tb200_ctx_sync(w->ctx)) { set_dev_err(); return 0; }
+  uint64_t total = 0;
+  uint64_t nb[8];
+  for (int s = 0; s < nsub; ++s)
+    {
+    nb[s] = codec == 1 ? ((const uint32_t*)sizes)[s] : sizes[s];
+    if (nb[s] == 0 || nb[s] > per || nb[s] > 0xffffffffull) { set_err("encoder returned an impossible size"); return 0; }
+    total += 4 + nb[s];
+    }
+  if (!buffer_reserve(a, total)) return 0;
+  for (int s = 0; s < nsub; ++s)
+    {
+    put32(a->buffer + a->size, (uint32_t)nb[s]);
+    if (!tb200_memcpy_d2h(w->ctx, a->buffer + a->size + 4, d_pay + per * s, nb[s])) { set_dev_err(); return 0; }
+    a->size += 4 + nb[s];
+    }
+  if (!tb200_ctx_sync(w->ctx)) { set_dev_err(); return 0; }
+  return 1;
+  }
+
 static int write_stream(void* h, int type, const void* data, uint32_t count)
   {
   archive* a = (archive*)h;
@@ -584,6 +672,7 @@ static int write_stream(void* h, int type, const void* data, uint32_t count)
   if (!codec) return 0;
   if (!need_worker(a)) return 0;
   worker* w = a->w;
+  if (a->format == 0) return write_stream_v0(a, type, data, count, codec, ws, nc, pc);
   int log2c = codec == 1 ? a->fpc_log2 : a->lz4_log2;
   if (codec == 1 && log2c && ws == 8 && log2c > 11) log2c = 11;
   if (codec == 2 && log2c && ws == 8 && log2c > 14) log2c = 14;
