@@ -96,6 +96,21 @@ def test_reference_clients_against_our_library():
         return np.ascontiguousarray(rec[:, 12:48]).view(np.float32)          # the three vertices of every facet
     a, b = tris(os.path.join(out, "data", "StanfordBunny.stl")), tris(os.path.join(out, "bunny_test_out.stl"))
     assert a.shape == b.shape and np.array_equal(a, b)
+    # the same unmodified encoder, told through the environment to write the reference's own format:
+    # the compiled reference library reads the archive the GPU wrote
+    env0 = dict(env); env0["TRICO_B200_FORMAT"] = "0"
+    r = subprocess.run(["./trico_encoder", "-i", "data/StanfordBunny.stl", "-o", "bunny_test_v0.trc"], cwd=out, env=env0, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-500:])
+    blob0, blob1 = open(os.path.join(out, "bunny_test_v0.trc"), "rb").read(), open(os.path.join(out, "bunny_test.trc"), "rb").read()
+    assert int.from_bytes(blob0[4:8], "little") == 0 and int.from_bytes(blob1[4:8], "little") == 1
+    from checkers import Oracle, TricoCApi, REF_SO, have_ref
+    orc = Oracle()
+    _, want = orc.read_archive(blob1)
+    _, got = orc.read_archive(blob0)
+    assert [(t, c) for t, c, _ in got] == [(t, c) for t, c, _ in want] and all(x[2].tobytes() == y[2].tobytes() for x, y in zip(got, want))
+    if have_ref():
+        _, got = TricoCApi(REF_SO).decode(blob0, orc)
+        assert all(x[2].tobytes() == y[2].tobytes() for x, y in zip(got, want))
 
 
 # --------------------------------------------------------- C3 / C4 / C5 shapes at >= 1 M elements
