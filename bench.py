@@ -475,7 +475,52 @@ def extras_single(B, steps):
         out["C5"] = c5_batch(B, max(2, steps // 2))
     except Exception as ex:
         out["C5"] = {"error": str(ex)}
+    try:
+        out["C2_reference_format"] = c2_reference_format(B, steps)
+    except Exception as ex:
+        out["C2_reference_format"] = {"error": str(ex)}
     return out
+
+
+def c2_reference_format(B, steps):
+    """The C2 mesh written in the REFERENCE's own format on the device (what trico_write_* do under
+    trico_b200_set_format(archive, 0)): every vertex component ONE FPC chain (tile-parallel encoder,
+    bytes identical to trico_compress), every index plane ONE LZ4 block (merged from the per-block results)."""
+    import ctypes as C
+    torch, d, lib = B.torch, B.d, B.lib
+    from trico_b200 import workloads as W
+    (_, _, v, nv), (_, _, t, nt) = W.c2(B.dev)
+    vp = C.c_void_p
+    bf = (lib.tb200_fpc_v0_bound(4, nv) + 255) & ~255
+    bl = (lib.tb200_lz4_v0_bound(t.numel()) + 255) & ~255
+    of = torch.empty(3 * bf, dtype=torch.uint8, device=B.dev)
+    ol = torch.empty(4 * bl, dtype=torch.uint8, device=B.dev)
+    nb = torch.zeros(16, dtype=torch.int64, device=B.dev)
+
+    def enc_f():
+        assert lib.tb200_fpc_encode_v0(d.ctx, 4, vp(v.data_ptr()), nv, 3, 3, 4, 10, vp(of.data_ptr()), bf, vp(nb.data_ptr()))
+
+    def enc_l():
+        assert lib.tb200_lz4_encode_v0(d.ctx, 4, vp(t.data_ptr()), t.numel(), vp(ol.data_ptr()), bl, vp(nb.data_ptr() + 64))
+
+    for _ in range(2):
+        enc_f(); enc_l()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * steps)]
+    for s in range(steps):
+        ev[3 * s].record(); enc_f(); ev[3 * s + 1].record(); enc_l(); ev[3 * s + 2].record()
+    torch.cuda.synchronize()
+    tf = sum(ev[3 * s].elapsed_time(ev[3 * s + 1]) for s in range(steps)) / steps / 1e3
+    tl = sum(ev[3 * s + 1].elapsed_time(ev[3 * s + 2]) for s in range(steps)) / steps / 1e3
+    h = nb.cpu().numpy()
+    fbytes = int(h[:2].view("uint32")[:3].sum())
+    lbytes = int(h[8:12].view("uint64").sum())
+    rawf, rawl = v.numel() * 4, t.numel() * 4
+    return {"workload": "C2 in the reference's own (version 0) format, device resident: 3 FPC chains of 100 M floats + 4 whole-plane LZ4 blocks of 600 M bytes",
+            "vertices_encode_gbs": round(rawf / tf / 1e9, 1), "triangles_encode_gbs": round(rawl / tl / 1e9, 1),
+            "encode_gbs": round((rawf + rawl) / (tf + tl) / 1e9, 1), "ratio": round((rawf + rawl) / (fbytes + lbytes + 8 + 10 + 28), 4),
+            "ratio_streams": {"vertices": round(rawf / fbytes, 4), "triangles": round(rawl / lbytes, 4)},
+            "steps": steps, "decode": "v0 streams are one serial chain per component / plane: read by the legacy kernels (K4L / K6L), not timed here"}
 
 
 def c5_batch(B, steps):
