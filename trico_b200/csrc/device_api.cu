@@ -44,9 +44,9 @@ struct tb200_ctx
   uint64_t launches;
   int max_smem_optin;
   // batches of streams run on several CUDA streams: sub-contexts, created on first use (device_api_misc.inc)
-  tb200_ctx* sub[7];
+  tb200_ctx* sub[31];
   int nsub;
-  cudaEvent_t ev_fork, ev_join[7];
+  cudaEvent_t ev_fork, ev_join[31];
   };
 
 extern "C" int tb200_device_count(void)
