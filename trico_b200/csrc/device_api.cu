@@ -301,7 +301,9 @@ static int launch_fpc_encode_lanes(tb200_ctx* c, FpcEncodeArgs a)
   if (!persistent_grid(fpc_encode_lanes_kernel<W, NCOMP, R, SB, EX, DF>, NWARPS * 32, smem, c, &per_sm, &sms)) return 0;
   if (per_sm < 1) return fail_msg("fpc_encode_lanes_kernel does not fit on an SM");
   // persistent grid, every CTA resident (the look-back relies on it); a CTA reuses its scratch slots
-  if (const char* e = getenv("TB200_FPC_ENC_CTAS")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments
+  static int ctas_cap = -1;                                                              // experiments
+  if (ctas_cap < 0) { const char* e = getenv("TB200_FPC_ENC_CTAS"); ctas_cap = e ? atoi(e) : 0; }
+  if (ctas_cap >= 1 && ctas_cap < per_sm) per_sm = ctas_cap;
   uint32_t grid = (uint32_t)per_sm * (uint32_t)sms;
   if (grid > a.ntiles) grid = a.ntiles;
   a.slot = slot;
