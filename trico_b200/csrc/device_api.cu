@@ -511,12 +511,12 @@ extern "C" int tb200_fpc_decode_v0(tb200_ctx* c, int wordsize, const uint8_t* d_
   if (wordsize == 4)
     {
     if (!set_smem(fpc_decode_legacy_kernel<uint32_t>, smem, c)) return 0;
-    fpc_decode_legacy_kernel<uint32_t><<<nstreams, 32, smem, c->stream>>>(a);
+    fpc_decode_legacy_kernel<uint32_t><<<nstreams, 64, smem, c->stream>>>(a);
     }
   else
     {
     if (!set_smem(fpc_decode_legacy_kernel<uint64_t>, smem, c)) return 0;
-    fpc_decode_legacy_kernel<uint64_t><<<nstreams, 32, smem, c->stream>>>(a);
+    fpc_decode_legacy_kernel<uint64_t><<<nstreams, 64, smem, c->stream>>>(a);
     }
   c->launches++;
   CK(cudaGetLastError());

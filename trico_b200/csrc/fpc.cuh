@@ -1439,26 +1439,31 @@ struct FpcLegacyDecodeArgs
 constexpr uint32_t FPC_LEGACY_RING = 4096;
 
 template <typename W>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(64)
 fpc_decode_legacy_kernel(const FpcLegacyDecodeArgs a)
   {
+  // Two warps.  Warp 1 FEEDS: it keeps the ring filled, parses the code words of step s and gathers
+  // its residuals into one half of a double buffer, and writes the values of step s - 2 out.  Lane 0
+  // of warp 0 runs the CHAIN of step s - 1 meanwhile - nothing but the two dependent table reads,
+  // the xor and the hash updates per value (fpc.c:308-326).  One CTA barrier per 32 values.
   using TR = FpcTraits<W>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* ring = smem_raw;                                        // FPC_LEGACY_RING bytes
-  __shared__ W sh_x[32], sh_v[32];
-  __shared__ uint32_t sh_u2[32];
-  const unsigned c = blockIdx.x, lane = lane_id();
+  __shared__ W sh_x[2][32], sh_v[2][32];
+  __shared__ uint32_t sh_u2[2][32];
+  const unsigned c = blockIdx.x, lane = lane_id(), warp = threadIdx.x >> 5;
   const uint8_t* p = a.streams[c];
   const int e1 = (p[0] >> 4) << 1, e2 = (p[0] & 15) << 1;          // fpc.c:214-217
   const uint32_t n = ((uint32_t)p[1] << 24) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 8) | p[4];
   const size_t nt1 = (size_t)1 << e1, nt2 = (size_t)1 << e2;
   W* T1; W* T2;
-  if (a.gtables == nullptr) { T1 = reinterpret_cast<W*>(smem_raw + FPC_LEGACY_RING); for (size_t i = lane; i < nt1 + nt2; i += 32) T1[i] = 0; }
+  if (a.gtables == nullptr) { T1 = reinterpret_cast<W*>(smem_raw + FPC_LEGACY_RING); for (size_t i = threadIdx.x; i < nt1 + nt2; i += 64) T1[i] = 0; }
   else T1 = reinterpret_cast<W*>(a.gtables) + (size_t)c * a.gtable_words;
   T2 = T1 + nt1;
-  if (lane == 0) a.counts[c] = n;
+  if (threadIdx.x == 0) a.counts[c] = n;
   const uint32_t todo = n < a.expect ? n : a.expect;
-  // the ring holds stream bytes [ring_lo, ring_hi) of the 16-byte aligned view of the stream
+  const uint32_t nsteps = (todo + 31u) / 32u;
+  // feeder state: the ring holds stream bytes [ring_lo, ring_hi) of the 16-byte aligned view of the stream
   const uint8_t* base = p - (reinterpret_cast<uintptr_t>(p) & 15u);
   const uint64_t readable = a.extents && a.extents[c] ? a.extents[c] + (uint64_t)(p - base) : ~0ull;   // from base
   const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
@@ -1474,70 +1479,78 @@ fpc_decode_legacy_kernel(const FpcLegacyDecodeArgs a)
     asm volatile("cp.async.commit_group;" ::: "memory");
     hi = upto;
     };
-  request(FPC_LEGACY_RING);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
   auto rb = [&](uint64_t o) -> uint32_t { return ring[o & (FPC_LEGACY_RING - 1)]; };
+  if (warp == 1)
+    {
+    request(FPC_LEGACY_RING);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+  __syncthreads();
 
   FpcLaneState<W> st; st.pred1 = 0; st.pred2 = 0; st.last = 0; st.c1 = 0; st.c2 = 0;
   const uint32_t m2 = (uint32_t)nt2 - 1;
   W* out = reinterpret_cast<W*>(a.out) + c;
   constexpr int GPS = 32 / TR::GROUP;                              // groups per step
   const uint32_t gl = lane % TR::GROUP, gi = lane / TR::GROUP;
-  for (uint32_t i0 = 0; i0 < todo; i0 += 32)
+  for (uint32_t s = 0; s < nsteps + 2u; ++s)
     {
-    // keep two kilobytes ahead: the half of the ring behind the read position is free
-    const uint64_t target = ((bp >> 11) + 2) << 11;
-    if (target > hi) request(target);
-    if (bp + 320 > hi - 2048) asm volatile("cp.async.wait_group 0;" ::: "memory");      // the step reaches into the newest half
-    else asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();
-    // code words of the step: every lane walks them, lane j keeps the place of residual j
-    uint64_t gp = bp, my_at = 0;
-    uint32_t my_nb = 0;
-    bool my_use2 = false;
+    if (warp == 1)
+      {
+      if (s < nsteps)
+        { // ---- feed step s ----
+        // keep two kilobytes ahead: the half of the ring behind the read position is free
+        const uint64_t target = ((bp >> 11) + 2) << 11;
+        if (target > hi) request(target);
+        if (bp + 320 > hi - 2048) asm volatile("cp.async.wait_group 0;" ::: "memory");      // the step reaches into the newest half
+        else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        // code words of the step: every lane walks them, lane j keeps the place of residual j
+        uint64_t gp = bp, my_at = 0;
+        uint32_t my_nb = 0;
+        bool my_use2 = false;
 #pragma unroll 1
-    for (int g = 0; g < GPS; ++g)
-      {
-      uint32_t bc = 0;
+        for (int g = 0; g < GPS; ++g)
+          {
+          uint32_t bc = 0;
 #pragma unroll
-      for (int b = 0; b < TR::HDR; ++b) bc = (bc << 8) | rb(gp + b);
-      uint32_t sum = 0;
+          for (int b = 0; b < TR::HDR; ++b) bc = (bc << 8) | rb(gp + b);
+          uint32_t sum = 0;
 #pragma unroll
-      for (int jj = 0; jj < TR::GROUP; ++jj)
-        {
-        const uint32_t code = (bc >> (TR::CBITS * jj)) & ((1u << TR::CBITS) - 1u);
-        const uint32_t nb = code > (uint32_t)TR::BASE2 ? code - TR::BASE2 : code;
-        if ((uint32_t)g == gi && (uint32_t)jj == gl) { my_at = gp + TR::HDR + sum; my_nb = nb; my_use2 = code > (uint32_t)TR::BASE2; }
-        sum += nb;
+          for (int jj = 0; jj < TR::GROUP; ++jj)
+            {
+            const uint32_t code = (bc >> (TR::CBITS * jj)) & ((1u << TR::CBITS) - 1u);
+            const uint32_t nb = code > (uint32_t)TR::BASE2 ? code - TR::BASE2 : code;
+            if ((uint32_t)g == gi && (uint32_t)jj == gl) { my_at = gp + TR::HDR + sum; my_nb = nb; my_use2 = code > (uint32_t)TR::BASE2; }
+            sum += nb;
+            }
+          gp += TR::HDR + sum;
+          }
+        // residual of value 32 s + lane, big-endian
+        W x = 0;
+        for (uint32_t b = 0; b < my_nb; ++b) x = (W)(x << 8) | (W)rb(my_at + b);
+        sh_x[s & 1u][lane] = x; sh_u2[s & 1u][lane] = my_use2 ? 1u : 0u;
+        bp = gp;          // (the pad slots of a last, incomplete group do not matter any more)
         }
-      gp += TR::HDR + sum;
+      if (s >= 2u)
+        { // ---- values of step s - 2 leave ----
+        const uint32_t i = 32u * (s - 2u) + lane;
+        if (i < todo) out[(size_t)i * a.stride] = sh_v[s & 1u][lane];
+        }
       }
-    // residual of value i0 + lane, big-endian
-    W x = 0;
-    for (uint32_t b = 0; b < my_nb; ++b) x = (W)(x << 8) | (W)rb(my_at + b);
-    __syncwarp();
-    // the chain: lane 0 only.  Residuals and predictor choices go through shared memory (their reads
-    // do not depend on the chain, so the unrolled loop has them in registers ahead of time); what is
-    // left per value is the chain itself: two dependent table reads, the xor and the two hash updates.
-    sh_x[lane] = x; sh_u2[lane] = my_use2 ? 1u : 0u;
-    __syncwarp();
-    if (lane == 0)
-      {
+    else if (lane == 0 && s >= 1u && s <= nsteps)
+      { // ---- the chain of step s - 1 ----
+      const uint32_t q = (s - 1u) & 1u;
+      const uint32_t i0 = 32u * (s - 1u);
       const uint32_t cnt = todo - i0 < 32u ? todo - i0 : 32u;
       if (cnt == 32u)
         {
 #pragma unroll 8
-        for (int j = 0; j < 32; ++j) sh_v[j] = fpc_decode_value<W, 1>(st, sh_x[j], sh_u2[j] != 0u, T1, T2, e1, e2, m2);
+        for (int j = 0; j < 32; ++j) sh_v[q][j] = fpc_decode_value<W, 1>(st, sh_x[q][j], sh_u2[q][j] != 0u, T1, T2, e1, e2, m2);
         }
       else
-        for (uint32_t j = 0; j < cnt; ++j) sh_v[j] = fpc_decode_value<W, 1>(st, sh_x[j], sh_u2[j] != 0u, T1, T2, e1, e2, m2);
+        for (uint32_t j = 0; j < cnt; ++j) sh_v[q][j] = fpc_decode_value<W, 1>(st, sh_x[q][j], sh_u2[q][j] != 0u, T1, T2, e1, e2, m2);
       }
-    __syncwarp();
-    const W mine = sh_v[lane];
-    if (i0 + lane < todo) out[(size_t)(i0 + lane) * a.stride] = mine;
-    // bytes of the values that exist (the pad slots of a last, incomplete group do not matter any more)
-    bp = gp;
+    __syncthreads();
     }
   }
 
