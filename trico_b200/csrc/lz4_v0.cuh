@@ -105,17 +105,31 @@ lz4_v0_scan_kernel(const Lz4V0Args a)
   uint32_t carry = 0;            // literals pending in front of the step
   uint64_t at = 0;               // bytes of the merged block so far
   uint32_t regions = 0;          // matches so far
+  // the loads of a step are requested one step ahead (a step is a dozen shuffles: the round trip to
+  // memory would be all of its time)
+  auto fetch = [&](uint32_t k, Lz4V0Meta& m, uint32_t& size)
+    {
+    m.tail = 0; m.first = 0; m.h_first = 0; m.h_tail = 0; m.has_match = 0; m.pad = 0; size = 0;
+    if (k < a.nranges)
+      {
+      const uint64_t g = (uint64_t)k * a.planes + p;
+      m = a.meta[g];
+      size = (uint32_t)a.sizes[2 * g] | ((uint32_t)a.sizes[2 * g + 1] << 8);
+      }
+    };
+  Lz4V0Meta m_next; uint32_t size_next;
+  fetch(lane, m_next, size_next);
   for (uint32_t k0 = 0; k0 < a.nranges; k0 += 32)
     {
     const uint32_t k = k0 + lane;
     const bool act = k < a.nranges;
     const uint64_t g = (uint64_t)k * a.planes + p;
-    Lz4V0Meta m; m.tail = 0; m.first = 0; m.h_first = 0; m.h_tail = 0; m.has_match = 0; m.pad = 0;
-    uint32_t size = 0, cnt = 0;
+    const Lz4V0Meta m = m_next;
+    const uint32_t size = size_next;
+    fetch(k + 32u, m_next, size_next);
+    uint32_t cnt = 0;
     if (act)
       {
-      m = a.meta[g];
-      size = (uint32_t)a.sizes[2 * g] | ((uint32_t)a.sizes[2 * g + 1] << 8);
       const uint64_t lo = (uint64_t)k << a.log2B;
       cnt = (uint32_t)(a.n - lo < B ? a.n - lo : B);
       }
@@ -176,23 +190,25 @@ lz4_v0_scan_kernel(const Lz4V0Args a)
   }
 
 __device__ __forceinline__ void lz4_v0_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n)
-  { // warp copy, any alignment on both sides: bytes up to the destination's 4-byte boundary, then words assembled from bytes pairs
+  { // warp copy, any alignment on both sides: bytes up to the destination's 16-byte boundary, then 16-byte
+    // stores assembled from five aligned source words each (the source may read up to 7 bytes past its
+    // end: the scratch slots have that slack)
   const unsigned lane = lane_id();
-  uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
+  uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
   if (head > n) head = n;
   if (lane < head) dst[lane] = __ldcg(src + lane);
-  const uint32_t nw = (n - head) >> 2;
+  const uint32_t nvec = (n - head) >> 4;
   const uint8_t* s = src + head;
-  uint32_t* d = reinterpret_cast<uint32_t*>(dst + head);
   const uint32_t sh = (uint32_t)((uintptr_t)s & 3u);
   const uint32_t* sw = reinterpret_cast<const uint32_t*>(s - sh);
-  for (uint32_t i = lane; i < nw; i += 32)
+  uint4* dv = reinterpret_cast<uint4*>(dst + head);
+  for (uint32_t i = lane; i < nvec; i += 32)
     {
-    const uint32_t w0 = __ldcg(sw + i);
-    const uint32_t w1 = sh ? __ldcg(sw + i + 1u) : 0u;
-    d[i] = __funnelshift_r(w0, w1, 8u * sh);
+    const uint32_t* q = sw + 4u * i;
+    const uint32_t w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2), w3 = __ldcg(q + 3), w4 = __ldcg(q + 4);
+    dv[i] = make_uint4(__funnelshift_r(w0, w1, 8u * sh), __funnelshift_r(w1, w2, 8u * sh), __funnelshift_r(w2, w3, 8u * sh), __funnelshift_r(w3, w4, 8u * sh));
     }
-  const uint32_t done = head + (nw << 2);
+  const uint32_t done = head + (nvec << 4);
   if (done + lane < n) dst[done + lane] = __ldcg(src + done + lane);
   }
 
