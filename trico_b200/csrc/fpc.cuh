@@ -117,14 +117,16 @@ __device__ __forceinline__ uint32_t fpc_encode_warp(SrcPtr src, uint32_t stride,
   uint32_t carry_ta = CONTINUE ? ta_before : 0u, carry_tb = CONTINUE ? tb_before : 0u;      // t[j-1], t[j-2] entering the window
   uint32_t obase = 0;
 
-  W vnext = lane < cnt ? (W)src[(size_t)lane * stride] : (W)0;      // loads run one window ahead
+  W vnext = lane < cnt ? (W)src[(size_t)lane * stride] : (W)0;      // loads run two windows ahead
+  W vnext2 = lane + 32u < cnt ? (W)src[(size_t)(lane + 32u) * stride] : (W)0;
   for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
     {
     const uint32_t j = i0 + lane;
     const bool full = i0 + 32 <= cnt;       // warp-uniform: every lane holds a value
     const bool act = full || j < cnt;
     const W v = vnext;
-    vnext = j + 32u < cnt ? (W)src[(size_t)(j + 32u) * stride] : (W)0;
+    vnext = vnext2;
+    vnext2 = j + 64u < cnt ? (W)src[(size_t)(j + 64u) * stride] : (W)0;
     W vprev = __shfl_up_sync(FULL, v, 1);
     if (lane == 0) vprev = carry_v;
 
@@ -389,13 +391,15 @@ fpc_encode_v0_tiles_kernel(const FpcV0TileArgs a)
       {
       W carry_v = pv1;
       uint32_t carry_ta = ta0, carry_tb = tb0;
-      W vnext = lane < cnt ? src[(size_t)(j0 + lane) * a.stride] : (W)0;       // one window ahead: the loads are strided and far
+      W vnext = lane < cnt ? src[(size_t)(j0 + lane) * a.stride] : (W)0;       // two windows ahead: the loads are strided and far
+      W vnext2 = lane + 32u < cnt ? src[(size_t)(j0 + lane + 32u) * a.stride] : (W)0;
       for (uint32_t i0 = 0; i0 < cnt; i0 += 32)
         {
         const uint32_t j = i0 + lane;
         const bool act = j < cnt;
         const W v = vnext;
-        vnext = j + 32u < cnt ? src[(size_t)(j0 + j + 32u) * a.stride] : (W)0;
+        vnext = vnext2;
+        vnext2 = j + 64u < cnt ? src[(size_t)(j0 + j + 64u) * a.stride] : (W)0;
         W vprev = __shfl_up_sync(FULL, v, 1);
         if (lane == 0) vprev = carry_v;
         const uint32_t c1 = (uint32_t)(vprev >> (TR::BITS - a.e1));
