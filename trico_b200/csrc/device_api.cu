@@ -423,7 +423,7 @@ extern "C" int tb200_fpc_encode_v0(tb200_ctx* c, int wordsize, const void* d_in,
       const uint64_t warps = grid * FPC_V0_WARPS;
       uint64_t run = ((uint64_t)t.ntiles * nstreams) / (4 * warps);
       if (run < 1) run = 1;
-      if (run > 8) run = 8;
+      if (run > 16384u / FPC_V0_TILE) run = 16384u / FPC_V0_TILE;     // 16 K values per run
       if (const char* e = getenv("TB200_FPC_V0_RUN")) { const int v = atoi(e); if (v >= 1 && v <= 64) run = v; }
       t.run = (uint32_t)run;
       t.nruns = (uint32_t)((t.ntiles + run - 1) / run);

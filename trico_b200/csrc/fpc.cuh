@@ -315,7 +315,10 @@ fpc_encode_legacy_kernel(const FpcLegacyEncodeArgs a)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_copy_global(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n);      // below
 
-constexpr uint32_t FPC_V0_TILE = 2048;
+#ifndef TB200_FPC_V0_TILE
+#define TB200_FPC_V0_TILE 512      // 2048: 193 GB/s, 1024: 230, 512: 250 on C2 (shared memory per warp sets the occupancy), 4096: 143
+#endif
+constexpr uint32_t FPC_V0_TILE = TB200_FPC_V0_TILE;
 constexpr int FPC_V0_WARPS = 4;
 
 struct FpcV0TileArgs
