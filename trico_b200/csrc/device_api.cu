@@ -37,8 +37,8 @@ struct tb200_ctx
   int device;
   cudaStream_t stream;
   bool own_stream;
-  uint8_t* ws;            // zeroed-per-launch scratch: [ticket (16 B) | descriptors]
-  size_t ws_bytes;
+  uint8_t* ws;            // zeroed scratch, handed out in slices: [ticket (16 B) | descriptors] per launch
+  size_t ws_bytes, ws_used;
   uint8_t* big;           // large scratch (legacy tables, plane buffers)
   size_t big_bytes;
   uint64_t launches;
@@ -102,7 +102,7 @@ extern "C" void tb200_ctx_trim(tb200_ctx* c)
   cudaStreamSynchronize(c->stream);
   if (c->ws) cudaFree(c->ws);
   if (c->big) cudaFree(c->big);
-  c->ws = nullptr; c->ws_bytes = 0; c->big = nullptr; c->big_bytes = 0;
+  c->ws = nullptr; c->ws_bytes = 0; c->ws_used = 0; c->big = nullptr; c->big_bytes = 0;
   }
 extern "C" uint64_t tb200_ctx_launch_count(tb200_ctx* c) { return c->launches; }
 
@@ -114,23 +114,36 @@ extern "C" int tb200_ctx_sync(tb200_ctx* c)
   }
 
 // workspace for one launch: 16-byte ticket block followed by `ntiles` 64-bit descriptors, zeroed.
+// Every launch gets a FRESH zeroed slice of the workspace; the buffer is cleared as a whole when it
+// has been used up (stream order: after every kernel that looked at the old slices).  A stream of a
+// few hundred kilobytes needs well under a kilobyte, so a batch of small streams pays one memset per
+// few hundred streams instead of one per stream (a launch-bound regime: DESIGN.md, batched streams).
 static int ws_prepare(tb200_ctx* c, uint64_t ntiles, uint32_t** ticket, uint64_t** desc)
   {
   const size_t need = 16 + (size_t)ntiles * 8;
-  if (need > c->ws_bytes)
+  const size_t take = (need + 255) & ~(size_t)255;
+  if (take > c->ws_bytes)
     {
     // the previous buffer may still be in use by queued kernels
     CK(cudaStreamSynchronize(c->stream));
     if (c->ws) CK(cudaFree(c->ws));
-    c->ws = nullptr; c->ws_bytes = 0;
-    size_t cap = need + need / 2 + 4096;
+    c->ws = nullptr; c->ws_bytes = 0; c->ws_used = 0;
+    size_t cap = take + take / 2 + 4096;
     if (cap < (256u << 10)) cap = 256u << 10;            // small streams never come back here (cudaFree stalls every thread's stream)
+    cap = (cap + 255) & ~(size_t)255;
     CK(cudaMalloc((void**)&c->ws, cap));
     c->ws_bytes = cap;
+    CK(cudaMemsetAsync(c->ws, 0, cap, c->stream));
     }
-  CK(cudaMemsetAsync(c->ws, 0, need, c->stream));
-  *ticket = reinterpret_cast<uint32_t*>(c->ws);
-  *desc = reinterpret_cast<uint64_t*>(c->ws + 16);
+  if (c->ws_used + take > c->ws_bytes)
+    {
+    CK(cudaMemsetAsync(c->ws, 0, c->ws_used, c->stream));
+    c->ws_used = 0;
+    }
+  uint8_t* p = c->ws + c->ws_used;
+  c->ws_used += take;
+  *ticket = reinterpret_cast<uint32_t*>(p);
+  *desc = reinterpret_cast<uint64_t*>(p + 16);
   return 1;
   }
 
