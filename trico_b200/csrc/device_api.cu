@@ -329,6 +329,42 @@ static int launch_fpc_encode_lanes(tb200_ctx* c, FpcEncodeArgs a)
   return 1;
   }
 
+static int launch_fpc_encode_small(tb200_ctx* c, const FpcEncodeArgs& f, int wordsize, int ncomp)
+  {
+  const uint32_t S = 1u << f.log2S;
+  const uint64_t nchunks = (uint64_t)f.nranges * ncomp;
+  const unsigned ntiles = (unsigned)((nchunks + LZ4_ASM_TILE - 1) / LZ4_ASM_TILE);
+  Lz4EncodeArgs a;                                  // the assembly kernel of the LZ4 path: chunk g at scratch + g * slot, u16 sizes
+  a.in = nullptr; a.n = 0; a.nranges = 0; a.log2B = 0; a.dense_list = nullptr; a.dense_count = nullptr; a.dbg = nullptr;
+  a.sizes = f.sizes; a.payload = f.payload; a.total = f.total;
+  a.slot = (fpc_chunk_bound(S, wordsize) + 16u + 15u) & ~15u;
+  if (!ws_prepare(c, (uint64_t)ntiles + 1, &a.ticket, &a.desc)) return 0;
+  a.total_field = f.total_field ? f.total_field : reinterpret_cast<uint8_t*>(a.desc + ntiles);
+  uint8_t* scratch = nullptr;
+  if (!big_prepare(c, (size_t)nchunks * a.slot + 64, &scratch)) return 0;
+  a.scratch = scratch;
+  FpcChunksArgs k;
+  k.in = f.in; k.n = f.n; k.nranges = f.nranges; k.log2S = f.log2S; k.e1 = f.e1; k.e2 = f.e2; k.ncomp = ncomp;
+  k.sizes = f.sizes; k.scratch = scratch; k.slot = a.slot;
+  const size_t tw = ((size_t)1 << f.e1) + ((size_t)1 << f.e2);
+  const size_t smem = ((((tw * wordsize) + 15) & ~(size_t)15) + a.slot + 16) * FPC_CHUNKS_WARPS;
+  const unsigned grid = (unsigned)((nchunks + FPC_CHUNKS_WARPS - 1) / FPC_CHUNKS_WARPS);
+  if (wordsize == 4)
+    {
+    if (!set_smem(fpc_encode_chunks_kernel<uint32_t>, smem, c)) return 0;
+    fpc_encode_chunks_kernel<uint32_t><<<grid, FPC_CHUNKS_WARPS * 32, smem, c->stream>>>(k);
+    }
+  else
+    {
+    if (!set_smem(fpc_encode_chunks_kernel<uint64_t>, smem, c)) return 0;
+    fpc_encode_chunks_kernel<uint64_t><<<grid, FPC_CHUNKS_WARPS * 32, smem, c->stream>>>(k);
+    }
+  lz4_assemble_kernel<<<ntiles, LZ4_ASM_THREADS, 0, c->stream>>>(a, nchunks);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  return 1;
+  }
+
 extern "C" int tb200_fpc_encode(tb200_ctx* c, int wordsize, int ncomp, const void* d_in, uint64_t n, int log2_chunk,
                                 int e1, int e2, uint8_t* d_sizes, uint8_t* d_payload, uint8_t* d_total_field, uint64_t* d_total)
   {
@@ -347,6 +383,12 @@ extern "C" int tb200_fpc_encode(tb200_ctx* c, int wordsize, int ncomp, const voi
     if (d_total_field) CK(cudaMemsetAsync(d_total_field, 0, 8, c->stream));
     return 1;
     }
+  // K3S: a stream of a few thousand chunks is all latency for the lane-per-chunk kernel (every lane
+  // encodes 512 values one after the other); a warp per chunk finishes in a tenth of the time
+  static int small_max = -1;
+  if (small_max < 0) { const char* e = getenv("TB200_FPC_SMALL_CHUNKS"); small_max = e ? atoi(e) : 8192; }
+  const uint64_t nchunks = (uint64_t)a.nranges * ncomp;
+  if (nchunks <= (uint64_t)small_max) return launch_fpc_encode_small(c, a, wordsize, ncomp);
   if (wordsize == 4)
     return ncomp == 3 ? launch_fpc_encode_lanes<uint32_t, 3, 1, 32>(c, a) : ncomp == 2 ? launch_fpc_encode_lanes<uint32_t, 2, 2, 32>(c, a) : launch_fpc_encode_lanes<uint32_t, 1, 4, 32>(c, a);
   return ncomp == 3 ? launch_fpc_encode_lanes<uint64_t, 3, 1, 16>(c, a) : ncomp == 2 ? launch_fpc_encode_lanes<uint64_t, 2, 2, 16>(c, a) : launch_fpc_encode_lanes<uint64_t, 1, 4, 16>(c, a);

@@ -287,6 +287,54 @@ fpc_encode_legacy_kernel(const FpcLegacyEncodeArgs a)
   }
 
 // ---------------------------------------------------------------------------------------------
+// K3S: chunked encode of SMALL streams, one WARP per chunk.  K3 (below) gives every lane a whole
+// chunk: 512 serial values per lane, ~150 us however few chunks the stream has - fine when a
+// stream fills the machine with lanes, all latency when it is the 117 chunks of a 20,000-vertex
+// mesh (C5: thousands of such streams).  Here a warp runs the warp-cooperative encoder
+// (fpc_encode_warp: 32 values per step, the same bytes) on its chunk: 16 steps instead of 512
+// values, the blocks go to scratch slots and lz4_assemble_kernel (the LZ4 path's assembly: sizes ->
+// offsets -> copy) lays them out.  Picked by the launcher for streams of at most 8192 chunks.
+// ---------------------------------------------------------------------------------------------
+struct FpcChunksArgs
+  {
+  const void* in;          // device, AoS: n * ncomp words
+  uint64_t n;              // values per component
+  uint32_t nranges;
+  int log2S, e1, e2, ncomp;
+  uint8_t* sizes;          // u16 LE [nranges * ncomp]
+  uint8_t* scratch;        // one slot per chunk
+  uint32_t slot;
+  };
+
+constexpr int FPC_CHUNKS_WARPS = 4;
+
+template <typename W>
+__global__ void __launch_bounds__(FPC_CHUNKS_WARPS * 32)
+fpc_encode_chunks_kernel(const FpcChunksArgs a)
+  {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t tw = (1u << a.e1) + (1u << a.e2);
+  const size_t per_warp = (((size_t)tw * sizeof(W) + 15) & ~(size_t)15) + a.slot + 16;
+  uint8_t* my = smem_raw + (size_t)warp * per_warp;
+  W* T1 = reinterpret_cast<W*>(my);
+  uint8_t* ob = my + (((size_t)tw * sizeof(W) + 15) & ~(size_t)15);
+  const uint64_t g = (uint64_t)blockIdx.x * FPC_CHUNKS_WARPS + warp;
+  if (g >= (uint64_t)a.nranges * a.ncomp) return;
+  const uint64_t k = g / a.ncomp;
+  const uint32_t c = (uint32_t)(g % a.ncomp);
+  const uint64_t lo = k << a.log2S;
+  const uint32_t S = 1u << a.log2S;
+  const uint32_t cnt = (uint32_t)(a.n - lo < S ? a.n - lo : S);
+  const W* src = reinterpret_cast<const W*>(a.in) + lo * a.ncomp + c;
+  const uint32_t nb = fpc_encode_warp<W, true>(src, (uint32_t)a.ncomp, cnt, ob, T1, T1 + (1u << a.e1), a.e1, a.e2);
+  __syncwarp();
+  uint4* sv = reinterpret_cast<uint4*>(a.scratch + g * a.slot);
+  for (uint32_t v4 = lane; v4 < (nb + 15u) >> 4; v4 += 32) sv[v4] = *reinterpret_cast<const uint4*>(ob + 16u * v4);
+  if (lane == 0) { a.sizes[2 * g] = (uint8_t)nb; a.sizes[2 * g + 1] = (uint8_t)(nb >> 8); }
+  }
+
+// ---------------------------------------------------------------------------------------------
 // K3L: TILE-PARALLEL encoder of reference-format (v0) streams - byte-identical to trico_compress
 // (fpc.c:86-210), many warps on ONE chain.
 //
