@@ -114,6 +114,20 @@ extern "C" int tb200_ctx_sync(tb200_ctx* c)
   }
 
 // workspace for one launch: 16-byte ticket block followed by `ntiles` 64-bit descriptors, zeroed.
+// tb200_encode_stream sets this around the codec call: a launcher that ends in lz4_assemble_kernel hands
+// the header fields to it (and says so); otherwise tb200_encode_stream launches the header kernel itself
+struct PendingHeader { uint8_t* out; uint32_t count; int type, info, log2; uint64_t fixed_plus_table; bool done; };
+static thread_local PendingHeader* tl_header = nullptr;
+static Lz4StreamHeader take_header()
+  {
+  Lz4StreamHeader a;
+  if (!tl_header) return a;
+  a.hdr = tl_header->out; a.hdr_count = tl_header->count; a.hdr_type = (uint8_t)tl_header->type; a.hdr_info = (uint8_t)tl_header->info;
+  a.hdr_log2 = (uint8_t)tl_header->log2; a.hdr_fixed_plus_table = tl_header->fixed_plus_table;
+  tl_header->done = true;
+  return a;
+  }
+
 // Every launch gets a FRESH zeroed slice of the workspace; the buffer is cleared as a whole when it
 // has been used up (stream order: after every kernel that looked at the old slices).  A stream of a
 // few hundred kilobytes needs well under a kilobyte, so a batch of small streams pays one memset per
@@ -359,7 +373,7 @@ static int launch_fpc_encode_small(tb200_ctx* c, const FpcEncodeArgs& f, int wor
     if (!set_smem(fpc_encode_chunks_kernel<uint64_t>, smem, c)) return 0;
     fpc_encode_chunks_kernel<uint64_t><<<grid, FPC_CHUNKS_WARPS * 32, smem, c->stream>>>(k);
     }
-  lz4_assemble_kernel<<<ntiles, LZ4_ASM_THREADS, 0, c->stream>>>(a, nchunks);
+  lz4_assemble_kernel<<<ntiles, LZ4_ASM_THREADS, 0, c->stream>>>(a, nchunks, take_header());
   c->launches += 2;
   CK(cudaGetLastError());
   return 1;

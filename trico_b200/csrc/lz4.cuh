@@ -722,6 +722,18 @@ struct Lz4EncodeArgs
   unsigned long long* dbg; // phase-cycle counters by plane (experiments; nullptr in production)
   };
 
+// whole v1 streams: the assembly's last tile also writes the fixed header fields (type, count, codec
+// info, chunk size; the payload byte count is total_field) and makes *total the STREAM's byte count -
+// a launch less per stream, which is what a batch of small streams is made of.  (Its own kernel
+// parameter: growing Lz4EncodeArgs cost lz4_encode_kernel 4 % on C2.)
+struct Lz4StreamHeader
+  {
+  uint8_t* hdr = nullptr;
+  uint32_t hdr_count = 0;
+  uint8_t hdr_type = 0, hdr_info = 0, hdr_log2 = 0;
+  uint64_t hdr_fixed_plus_table = 0;
+  };
+
 constexpr int LZ4_HLOG = 10;     // default: 1024 u16 entries = 2 KiB per warp (12 resident warps per SM with 16 KiB blocks)
 template <int WB> struct Lz4Cta { static constexpr int WARPS = WB > 4 ? WB : 4; };
 
@@ -902,7 +914,7 @@ constexpr int LZ4_ASM_TILE = 128;           // 64 measured the same, 256 slower
 
 #ifndef TB200_HOST_EMU
 __global__ void __launch_bounds__(LZ4_ASM_THREADS)
-lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
+lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks, const Lz4StreamHeader h)
   {
   __shared__ uint32_t sh_off[LZ4_ASM_TILE];
   __shared__ uint32_t sh_sz[LZ4_ASM_TILE];
@@ -940,7 +952,18 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks)
     if (lane == 0)
       {
       sh_base = excl;
-      if (tile == gridDim.x - 1) { *a.total = excl + tsum; store_u64_bytes(a.total_field, excl + tsum); }
+      if (tile == gridDim.x - 1)
+        {
+        store_u64_bytes(a.total_field, excl + tsum);
+        if (h.hdr)
+          {
+          h.hdr[0] = h.hdr_type;
+          h.hdr[1] = (uint8_t)h.hdr_count; h.hdr[2] = (uint8_t)(h.hdr_count >> 8); h.hdr[3] = (uint8_t)(h.hdr_count >> 16); h.hdr[4] = (uint8_t)(h.hdr_count >> 24);
+          h.hdr[5] = h.hdr_info; h.hdr[6] = h.hdr_log2;
+          *a.total = h.hdr_fixed_plus_table + excl + tsum;
+          }
+        else *a.total = excl + tsum;
+        }
       }
     }
   __syncthreads();
