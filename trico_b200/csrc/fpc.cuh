@@ -1029,6 +1029,9 @@ __device__ __forceinline__ void warp_copy_global(uint8_t* __restrict__ dst, cons
 #ifndef TB200_FPC_ENC_PREFETCH
 #define TB200_FPC_ENC_PREFETCH 1
 #endif
+#ifndef TB200_FPC_ENC_TMA
+#define TB200_FPC_ENC_TMA 1         // the slab arrives as one bulk copy (TMA, 1-D) per row, completion on an mbarrier
+#endif
 #ifndef TB200_FPC_ENC_WARPS
 #define TB200_FPC_ENC_WARPS 15      // resident warps per SM the register allocation aims at
 #endif
@@ -1037,6 +1040,34 @@ __device__ __forceinline__ void warp_copy_global(uint8_t* __restrict__ dst, cons
 // lanes encode (needs two sets of scratch slots per CTA).  Neither the look-back of the tile - its
 // predecessors finish at about the same time, so it used to wait for the slowest of the wave - nor
 // the read-back of the slots is waited for any more.
+// mbarrier + 1-D bulk copy (TMA) helpers of the encoder's slab staging: one `cp.async.bulk` per staged
+// row replaces 24 16-byte cp.async copies (and their address arithmetic in every thread); the bytes
+// are counted on an mbarrier every thread polls for itself, so the CTA barrier in front of the encode
+// goes as well.
+__device__ __forceinline__ void mbar_init(uint32_t mbar_s, uint32_t count)
+  {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar_s), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar_s, uint32_t bytes)
+  {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_s), "r"(bytes) : "memory");
+  }
+__device__ __forceinline__ void mbar_wait(uint32_t mbar_s, uint32_t parity)
+  {
+  uint32_t done;
+  do
+    {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(mbar_s), "r"(parity) : "memory");
+    } while (!done);
+  }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t mbar_s, uint64_t policy)
+  {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               :: "r"(dst_s), "l"(src), "r"(bytes), "r"(mbar_s), "l"(policy) : "memory");
+  }
+
 template <typename W, int NCOMP, int R, int SB, int EXP, bool DEFER>
 #ifdef TB200_FPC_ENC_MAXNREG
 __global__ void __maxnreg__(TB200_FPC_ENC_MAXNREG)
@@ -1071,9 +1102,13 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
   __shared__ uint32_t sh_off_p[DEFER ? NTHREADS : 1];
   __shared__ uint32_t sh_tsum_p;
   __shared__ uint64_t sh_base_p;
+  __shared__ __align__(8) uint64_t sh_mbar;               // counts the bytes of the slab in flight (TMA staging)
 
   const unsigned warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t c = warp % NCOMP, rgrp = warp / NCOMP;
+  const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&sh_mbar);
+  uint32_t slab_phase = 0;                                // parity of the slab the CTA waits for next (uniform)
+  if (TB200_FPC_ENC_TMA && threadIdx.x == 0) mbar_init(mbar_s, 1);   // the tile loop's first barrier publishes it
   const uint32_t klocal = rgrp * 32 + lane;
   const uint32_t S = 1u << a.log2S;
   const uint32_t h2 = (uint32_t)e2 >> 1, m2 = nt2 - 1;
@@ -1196,11 +1231,22 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
         {
         const uint8_t* tin = gin + (lo0 + i0) * (NCOMP * sizeof(W));
         const uint32_t row_bytes = (uint32_t)(NCOMP * sizeof(W)) << a.log2S;
+#if TB200_FPC_ENC_TMA
+        if (warp == 0)
+          { // lane = row: 16 * ROWV bytes each, all counted on the CTA's mbarrier
+          if (lane == 0) mbar_expect_tx(mbar_s, 32u * R * ROWV * 16u);
+          __syncwarp();
+#pragma unroll
+          for (uint32_t r = lane; r < 32u * R; r += 32)
+            bulk_g2s(stage_s + r * (uint32_t)ROWW * 4u, tin + (size_t)r * row_bytes, (uint32_t)ROWV * 16u, mbar_s, pol_first);
+          }
+#else
         for (uint32_t ci = threadIdx.x; ci < 32u * R * ROWV; ci += NTHREADS)
           {
           const uint32_t r = ci / (uint32_t)ROWV, v = ci - r * (uint32_t)ROWV;
           asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(stage_s + (r * ROWW + 4u * v) * 4u), "l"(tin + (size_t)r * row_bytes + 16u * v), "l"(pol_first) : "memory");
           }
+#endif
 #if TB200_FPC_ENC_PREFETCH
         // the slab after this one -> L2 (one 128-byte line per thread), so that its copy, issued one
         // sub-block from now, finds the data on the chip instead of waiting for DRAM
@@ -1233,7 +1279,12 @@ fpc_encode_lanes_kernel(const FpcEncodeArgs a)
     for (uint32_t i0 = 0; i0 < cnt0; i0 += SB)
       {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
+      if (TB200_FPC_ENC_TMA && fast_in)
+        { // every thread sees the slab's bytes arrive for itself: no CTA barrier in front of the encode
+        mbar_wait(mbar_s, slab_phase);
+        slab_phase ^= 1u;
+        }
+      else __syncthreads();
       if (DEFER && pv_valid)
         { // a piece of the previous tile: the chunk that arrived in the bounce buffer leaves, the next one is requested
         if (!pv_have_base && i0 >= (uint32_t)SB) pv_lookback();      // one sub-block after the tile's end its predecessors have published
