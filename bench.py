@@ -450,6 +450,39 @@ def c1_through_api(B):
             "ratio_reference": round(raw / (int(z["v0_archive"].size) - 8), 4), "encode_ms_per_archive": round((t1 - t0) / reps * 1e3, 3)}
 
 
+def stl_frontend(B):
+    """the tools' STL reader on the GPU - facets of the bunny, replicated with offsets, parsed and
+    de-duplicated (sort + unique + index remap, trico_io/iostl.c:70-138) device resident; wall clock around
+    tb200_stl_dedup, which allocates its scratch and synchronises.  tools/stl_speed.py times the reference beside it."""
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bunny_full.npz"))
+    v, t = z["vertices"], z["triangles"]
+    reps = 40
+    corners = v[t.reshape(-1)].reshape(-1, 9)
+    rec = np.zeros((reps, corners.shape[0], 50), np.uint8)
+    for r in range(reps):
+        c = corners.copy()
+        c[:, 0::3] += np.float32(0.25 * r)
+        rec[r, :, 12:48] = c.view(np.uint8).reshape(-1, 36)
+    nt = reps * corners.shape[0]
+    d = B.d
+    d_f, d_v, d_t = d.upload(rec.reshape(-1)), d.alloc(nt * 36), d.alloc(nt * 12)
+    best, nv = 1e9, 0
+    for it in range(4):
+        t0 = time.perf_counter()
+        nv = d.stl_dedup_device(d_f.ptr, nt, d_v.ptr, d_t.ptr)
+        if it:
+            best = min(best, time.perf_counter() - t0)
+    # the first copy is the bunny itself: its vertices and indices must come back where the reference put them
+    tri = d.download(d_t.ptr, nt * 12).view(np.uint32).reshape(reps, -1, 3)
+    ver = d.download(d_v.ptr, nv * 12).view(np.float32).reshape(-1, 3)
+    same = bool(np.array_equal(ver[tri[0]], v[t]))
+    return {"workload": "binary-STL facets of the bunny x %d (%d triangles) -> indexed mesh, device resident" % (reps, nt),
+            "triangles": nt, "vertices": int(nv), "ms": round(best * 1e3, 3), "mtriangles_per_s": round(nt / best / 1e6, 1),
+            "stl_gbs": round(nt * 50 / best / 1e9, 2), "sort_passes": int(d.lib.tb200_stl_last_sort_passes()),
+            "first_copy_matches_reference_mesh": same}
+
+
 def extras_single(B, steps):
     """the other BASELINE configurations on one GPU, device resident"""
     from trico_b200 import workloads as W
@@ -475,6 +508,10 @@ def extras_single(B, steps):
         out["C5"] = c5_batch(B, max(2, steps // 2))
     except Exception as ex:
         out["C5"] = {"error": str(ex)}
+    try:
+        out["stl_frontend"] = stl_frontend(B)
+    except Exception as ex:
+        out["stl_frontend"] = {"error": str(ex)}
     try:
         out["C2_reference_format"] = c2_reference_format(B, steps)
     except Exception as ex:

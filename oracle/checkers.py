@@ -383,3 +383,73 @@ class Ref(TricoCApi):
 
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
+
+
+# ---- mesh front-end: STL facets, de-duplication, normals --------------------------------
+
+def stl_facets(vertices: np.ndarray, triangles: np.ndarray, normals=None, attrs=None) -> np.ndarray:
+    """facet records of a binary STL file (iostl.c:261-320 layout): [nt, 50] bytes"""
+    vertices = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+    triangles = np.ascontiguousarray(triangles, np.uint32).reshape(-1, 3)
+    nt = triangles.shape[0]
+    rec = np.zeros((nt, 50), np.uint8)
+    if normals is not None:
+        rec[:, 0:12] = np.ascontiguousarray(normals, np.float32).reshape(nt, 3).view(np.uint8).reshape(nt, 12)
+    rec[:, 12:48] = vertices[triangles.reshape(-1)].reshape(nt, 9).view(np.uint8).reshape(nt, 36)
+    if attrs is not None:
+        rec[:, 48:50] = np.ascontiguousarray(attrs, np.uint16).reshape(nt, 1).view(np.uint8).reshape(nt, 2)
+    return rec
+
+
+def stl_file_bytes(facets: np.ndarray, header: bytes = b"binary stl written by the trico_b200 tests") -> bytes:
+    facets = np.ascontiguousarray(facets, np.uint8).reshape(-1, 50)
+    return header.ljust(80, b" ")[:80] + np.uint32(facets.shape[0]).tobytes() + facets.tobytes()
+
+
+def oracle_stl_dedup(oracle: "Oracle", facets: np.ndarray):
+    L = oracle.lib
+    L.oracle_stl_dedup.restype = C.c_uint32
+    L.oracle_stl_dedup.argtypes = [vp, C.c_uint32, vp, vp]
+    facets = np.ascontiguousarray(facets, np.uint8).reshape(-1, 50)
+    nt = facets.shape[0]
+    v = np.zeros((max(nt, 1) * 3, 3), np.float32)
+    t = np.zeros((nt, 3), np.uint32)
+    nv = L.oracle_stl_dedup(_ptr(facets), nt, _ptr(v), _ptr(t))
+    return v[:nv].copy(), t
+
+
+def oracle_triangle_normals(oracle: "Oracle", vertices: np.ndarray, triangles: np.ndarray) -> np.ndarray:
+    L = oracle.lib
+    L.oracle_triangle_normals.restype = None
+    L.oracle_triangle_normals.argtypes = [vp, vp, C.c_uint32, vp]
+    vertices = np.ascontiguousarray(vertices, np.float32)
+    triangles = np.ascontiguousarray(triangles, np.uint32).reshape(-1, 3)
+    out = np.zeros((triangles.shape[0], 3), np.float32)
+    L.oracle_triangle_normals(_ptr(vertices), _ptr(triangles), triangles.shape[0], _ptr(out))
+    return out
+
+
+def c_read_stl(lib_path: str, filename: str, full: bool = False):
+    """trico_read_stl / trico_read_stl_full of a library with the reference's trico_io signatures"""
+    L = C.CDLL(lib_path)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [vp]
+    nv, nt = C.c_uint32(0), C.c_uint32(0)
+    pv, pt, pn, pa = vp(), vp(), vp(), vp()
+    if full:
+        L.trico_read_stl_full.argtypes = [C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_char_p]
+        ok = L.trico_read_stl_full(C.byref(nv), C.byref(pv), C.byref(nt), C.byref(pt), C.byref(pn), C.byref(pa), filename.encode())
+    else:
+        L.trico_read_stl.argtypes = [C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(vp), C.c_char_p]
+        ok = L.trico_read_stl(C.byref(nv), C.byref(pv), C.byref(nt), C.byref(pt), filename.encode())
+    if not ok:
+        return None
+
+    def take(p, count, dtype):
+        if not (count and p.value):
+            return np.zeros(0, dtype)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize,)).copy().view(dtype)
+    out = (take(pv, nv.value * 3, np.float32).reshape(-1, 3), take(pt, nt.value * 3, np.uint32).reshape(-1, 3))
+    if full:
+        out += (take(pn, nt.value * 3, np.float32).reshape(-1, 3), take(pa, nt.value, np.uint16))
+    return out

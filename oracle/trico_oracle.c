@@ -566,3 +566,71 @@ uint64_t oracle_v1_read_stream(void* out, const uint8_t* in, uint64_t avail, int
     }
   return (uint64_t)(end - in);
   }
+
+/* =============================================================================================
+ * Mesh front-end: what trico_read_stl does after reading the facets, and the
+ * normal recomputation of trico_decoder.
+ * ============================================================================================= */
+#include <math.h>
+
+typedef struct { float x, y, z; uint32_t id; } oracle_corner;
+
+/* iostl.c:8-19 (less) with the corner id as the tie-break that makes the order total */
+static int oracle_corner_cmp(const void* pa, const void* pb)
+  {
+  const oracle_corner* a = (const oracle_corner*)pa;
+  const oracle_corner* b = (const oracle_corner*)pb;
+  if (a->x != b->x) return a->x < b->x ? -1 : 1;
+  if (a->y != b->y) return a->y < b->y ? -1 : 1;
+  if (a->z != b->z) return a->z < b->z ? -1 : 1;
+  return a->id < b->id ? -1 : (a->id > b->id ? 1 : 0);
+  }
+
+uint32_t oracle_stl_dedup(const uint8_t* facets, uint32_t ntriangles, float* vertices, uint32_t* triangles)
+  {
+  if (ntriangles == 0) return 0;                                     /* iostl.c:72-73 */
+  const uint64_t n = (uint64_t)ntriangles * 3;
+  oracle_corner* c = (oracle_corner*)malloc(n * sizeof(oracle_corner));
+  for (uint32_t t = 0; t < ntriangles; ++t)                           /* iostl.c:78-102: corner = position + its slot */
+    for (int j = 0; j < 3; ++j)
+      {
+      oracle_corner* q = c + (uint64_t)t * 3 + j;
+      memcpy(&q->x, facets + (uint64_t)t * 50 + 12 + 12 * j, 12);    /* iostl.c:175-183 */
+      q->id = t * 3 + (uint32_t)j;
+      }
+  qsort(c, n, sizeof(oracle_corner), oracle_corner_cmp);              /* iostl.c:104 */
+  uint32_t nv = 0;                                                    /* iostl.c:107-137: a new vertex where neighbours differ */
+  for (uint64_t i = 0; i < n; ++i)
+    {
+    if (i == 0 || !(c[i].x == c[i - 1].x && c[i].y == c[i - 1].y && c[i].z == c[i - 1].z))
+      {
+      vertices[(uint64_t)nv * 3] = c[i].x; vertices[(uint64_t)nv * 3 + 1] = c[i].y; vertices[(uint64_t)nv * 3 + 2] = c[i].z;
+      ++nv;
+      }
+    triangles[c[i].id] = nv - 1;
+    }
+  free(c);
+  return nv;
+  }
+
+void oracle_triangle_normals(const float* vertices, const uint32_t* triangles, uint32_t ntriangles, float* normals)
+  {
+  for (uint32_t t = 0; t < ntriangles; ++t)
+    {
+    const float* p0 = vertices + (uint64_t)triangles[(uint64_t)t * 3] * 3;
+    const float* p1 = vertices + (uint64_t)triangles[(uint64_t)t * 3 + 1] * 3;
+    const float* p2 = vertices + (uint64_t)triangles[(uint64_t)t * 3 + 2] * 3;
+    /* volatile: every operation rounded to float on its own, whatever the compiler flags (main.c:455-464) */
+    volatile float ax = p1[0] - p0[0], ay = p1[1] - p0[1], az = p1[2] - p0[2];
+    volatile float bx = p2[0] - p0[0], by = p2[1] - p0[1], bz = p2[2] - p0[2];
+    volatile float m0 = ay * bz, m1 = az * by, m2 = az * bx, m3 = ax * bz, m4 = ax * by, m5 = ay * bx;
+    volatile float nx = m0 - m1, ny = m2 - m3, nz = m4 - m5;
+    volatile float s0 = nx * nx, s1 = ny * ny, s2 = nz * nz;
+    volatile float s01 = s0 + s1;
+    volatile float s = s01 + s2;
+    const float length = (float)sqrt((double)s);                      /* main.c:465 */
+    normals[(uint64_t)t * 3] = length ? nx / length : nx;
+    normals[(uint64_t)t * 3 + 1] = length ? ny / length : ny;
+    normals[(uint64_t)t * 3 + 2] = length ? nz / length : nz;
+    }
+  }

@@ -87,6 +87,17 @@ uint64_t oracle_v1_stream_bound(int type, uint32_t count, int log2_chunk);
 uint64_t oracle_v1_write_stream(uint8_t* out, int type, const void* data, uint32_t count, int log2_chunk, int e1, int e2);
 uint64_t oracle_v1_read_stream(void* out, const uint8_t* in, uint64_t avail, int* type, uint32_t* count);
 
+/* ---- mesh front-end: STL vertex de-duplication and triangle normals ---- */
+/* iostl.c:70-138 (trico_remove_duplicate_vertices) on the facets of a binary STL file (50 bytes
+ * each: normal, three corners, attribute word - iostl.c:171-186).  Writes the unique vertices in
+ * (x, y, z) float order (comparator iostl.c:8-19, equality :21-26) and 3 indices per facet;
+ * vertices must hold 9*ntriangles floats.  Among corners that compare equal (+0 / -0) the lowest
+ * corner id supplies the bits (the reference's unstable quicksort leaves this open).
+ * Returns the number of vertices. */
+uint32_t oracle_stl_dedup(const uint8_t* facets, uint32_t ntriangles, float* vertices, uint32_t* triangles);
+/* tools/trico_decoder/main.c:441-469 */
+void oracle_triangle_normals(const float* vertices, const uint32_t* triangles, uint32_t ntriangles, float* normals);
+
 #ifdef __cplusplus
 }
 #endif

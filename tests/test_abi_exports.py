@@ -28,7 +28,7 @@ def test_headers_declare_the_reference_surface():
 def test_library_exports_every_declared_symbol():
     import trico_b200
     lib = trico_b200.load()
-    for header in ("trico_b200.h", "trico_b200_device.h"):
+    for header in ("trico_b200.h", "trico_b200_device.h", "trico_b200_io.h"):
         names = _declared(header)
         assert names
         for n in names:

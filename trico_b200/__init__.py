@@ -89,6 +89,15 @@ def load() -> C.CDLL:
         "tb200_encode_stream_sharded": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, _vp, C.POINTER(C.c_float)]),
         "tb200_comm_local_share": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(C.c_uint64)]),
         "tb200_decode_stream_range": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
+        # mesh front-end (include/trico_b200_io.h)
+        "tb200_stl_dedup": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint32)]),
+        "tb200_stl_dedup_scratch_bytes": (C.c_uint64, [C.c_uint32]),
+        "tb200_stl_last_sort_passes": (C.c_int, []),
+        "tb200_triangle_normals": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp]),
+        "trico_b200_triangle_normals": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp]),
+        "trico_read_stl": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(_vp), C.POINTER(C.c_uint32), C.POINTER(_vp), C.c_char_p]),
+        "trico_read_stl_full": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(_vp), C.POINTER(C.c_uint32), C.POINTER(_vp),
+                                          C.POINTER(_vp), C.POINTER(_vp), C.c_char_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -174,6 +183,40 @@ class Device:
         w, nc, pc = C.c_int(0), C.c_int(0), C.c_int(0)
         codec = self.lib.tb200_stream_layout(stream_type, C.byref(w), C.byref(nc), C.byref(pc))
         return dict(codec=codec, wordsize=w.value, ncomp=nc.value, per_count=pc.value)
+
+    # -- mesh front-end (include/trico_b200_io.h; reference trico_io/iostl.c:70-138) -------
+    def stl_dedup_device(self, d_facets: int, ntriangles: int, d_vertices: int, d_triangles: int, d_normals: int = 0, d_attrs: int = 0) -> int:
+        nv = C.c_uint32(0)
+        self._ck(self.lib.tb200_stl_dedup(self.ctx, _vp(d_facets), ntriangles, _vp(d_vertices), _vp(d_triangles),
+                                          _vp(d_normals) if d_normals else None, _vp(d_attrs) if d_attrs else None, C.byref(nv)))
+        return nv.value
+
+    def stl_dedup(self, facets, full: bool = False):
+        """host facet records (ntriangles x 50 bytes) -> (vertices [nv,3] f32, triangles [nt,3] u32[, normals, attributes])"""
+        facets = np.ascontiguousarray(facets, dtype=np.uint8).reshape(-1, 50)
+        nt = facets.shape[0]
+        if nt == 0:
+            empty = (np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32))
+            return empty + ((np.zeros((0, 3), np.float32), np.zeros(0, np.uint16)) if full else ())
+        d_f, d_v, d_t = self.upload(facets), self.alloc(nt * 36), self.alloc(nt * 12)
+        d_n, d_a = (self.alloc(nt * 12), self.alloc(nt * 2)) if full else (None, None)
+        nv = self.stl_dedup_device(d_f.ptr, nt, d_v.ptr, d_t.ptr, d_n.ptr if full else 0, d_a.ptr if full else 0)
+        out = (self.download(d_v.ptr, nv * 12).view(np.float32).reshape(-1, 3), self.download(d_t.ptr, nt * 12).view(np.uint32).reshape(-1, 3))
+        if full:
+            out += (self.download(d_n.ptr, nt * 12).view(np.float32).reshape(-1, 3), self.download(d_a.ptr, nt * 2).view(np.uint16))
+        return out
+
+    def triangle_normals(self, vertices, triangles) -> np.ndarray:
+        """tools/trico_decoder/main.c:439-470 on the device, bit for bit"""
+        vertices = np.ascontiguousarray(vertices, dtype=np.float32)
+        triangles = np.ascontiguousarray(triangles, dtype=np.uint32)
+        nt = triangles.size // 3
+        if nt == 0:
+            return np.zeros((0, 3), np.float32)
+        d_v, d_t, d_n = self.upload(vertices), self.upload(triangles), self.alloc(nt * 12)
+        self._ck(self.lib.tb200_triangle_normals(self.ctx, _vp(d_v.ptr), _vp(d_t.ptr), nt, _vp(d_n.ptr)))
+        self.sync()
+        return self.download(d_n.ptr, nt * 12).view(np.float32).reshape(-1, 3)
 
     # -- whole v1 streams (device resident) ------------------------------------------------
     def encode_stream_device(self, stream_type: int, d_data: int, count: int, d_out: int, out_cap: int, d_bytes: int, log2_chunk: int = 0):
@@ -292,3 +335,30 @@ class Device:
         d_s.free()
         d_o.free()
         return out
+
+
+def read_stl(filename: str, full: bool = False):
+    """trico_read_stl / trico_read_stl_full of the B200 library (reference trico_io/iostl.c:141, :197):
+    binary STL file -> (vertices [nv,3] f32, triangles [nt,3] u32[, normals [nt,3] f32, attributes [nt] u16])."""
+    L = load()
+    libc = C.CDLL(None)
+    libc.free.argtypes = [_vp]
+    nv, nt = C.c_uint32(0), C.c_uint32(0)
+    pv, pt, pn, pa = _vp(), _vp(), _vp(), _vp()
+    if full:
+        ok = L.trico_read_stl_full(C.byref(nv), C.byref(pv), C.byref(nt), C.byref(pt), C.byref(pn), C.byref(pa), filename.encode())
+    else:
+        ok = L.trico_read_stl(C.byref(nv), C.byref(pv), C.byref(nt), C.byref(pt), filename.encode())
+    if not ok:
+        raise TB200Error(L.tb200_last_error().decode() or "trico_read_stl failed")
+
+    def take(p, count, dtype):
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize,)).copy().view(dtype) \
+            if count and p.value else np.zeros(0, dtype)
+        if p.value:
+            libc.free(p)
+        return a
+    out = (take(pv, nv.value * 3, np.float32).reshape(-1, 3), take(pt, nt.value * 3, np.uint32).reshape(-1, 3))
+    if full:
+        out += (take(pn, nt.value * 3, np.float32).reshape(-1, 3), take(pa, nt.value, np.uint16))
+    return out

@@ -1,6 +1,7 @@
 // device_api.cu - thin extern "C" layer over the sm_100a kernels (include/trico_b200_device.h).
 // Owns the CUDA stream, the per-context workspace and every kernel launch.  No CPU fallback.
 #include "../../include/trico_b200_device.h"
+#include "../../include/trico_b200_io.h"
 
 #include "common.cuh"
 #include "fpc.cuh"
@@ -9,6 +10,7 @@
 #include "lz4_multi.cuh"
 #include "lz4_v0.cuh"
 #include "planes.cuh"
+#include "stl.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -597,3 +599,4 @@ extern "C" int tb200_fpc_decode_v0(tb200_ctx* c, int wordsize, const uint8_t* d_
 #include "device_api_lz4.inc"
 #include "device_api_misc.inc"
 #include "device_api_comm.inc"
+#include "device_api_stl.inc"
