@@ -10,6 +10,7 @@
  *   trico_read_stl_full   replaces /root/reference/trico_io/iostl.c:197-259
  *   (both call trico_remove_duplicate_vertices, iostl.c:70-138: quicksort :60-68 under the
  *    comparator :8-19, walk :107-137)
+ *   trico_write_stl       replaces /root/reference/trico_io/iostl.c:261-320
  *   trico_b200_triangle_normals   replaces the loop at /root/reference/tools/trico_decoder/main.c:439-470
  *
  * Same names, arguments, return values and ownership as the reference: buffers handed back come
@@ -35,6 +36,11 @@ TB200_API int trico_read_stl(uint32_t* nr_of_vertices, float** vertices, uint32_
 TB200_API int trico_read_stl_full(uint32_t* nr_of_vertices, float** vertices, uint32_t* nr_of_triangles, uint32_t** triangles,
                                   float** normals, uint16_t** attributes, const char* filename);
 
+/* Indexed mesh -> binary STL file, byte for byte the file the reference writes (iostl.c:261-320): NULL normals
+ * are written as zeros, NULL attributes as zero words.  The facets are gathered on the device. */
+TB200_API int trico_write_stl(const float* vertices, const uint32_t* triangles, const uint32_t nr_of_triangles,
+                              const float* triangle_normals, const uint16_t* attributes, const char* filename);
+
 /* Triangle normals from an indexed mesh, host buffers, bit-identical to the reference decoder's loop. */
 TB200_API int trico_b200_triangle_normals(const float* vertices, uint32_t nr_of_vertices, const uint32_t* triangles,
                                           uint32_t nr_of_triangles, float* triangle_normals);
@@ -52,6 +58,10 @@ TB200_API int tb200_stl_dedup(tb200_ctx* ctx, const uint8_t* d_facets, uint32_t 
 TB200_API uint64_t tb200_stl_dedup_scratch_bytes(uint32_t ntriangles);
 /* how many of the twelve 8-bit sort passes the last tb200_stl_dedup of this thread ran (the rest had one digit) */
 TB200_API int tb200_stl_last_sort_passes(void);
+/* d_facets (50 * ntriangles bytes, 2-byte aligned) <- the facet records of trico_write_stl; d_normals and
+ * d_attributes may be NULL */
+TB200_API int tb200_stl_facets(tb200_ctx* ctx, const float* d_vertices, const uint32_t* d_triangles, uint32_t ntriangles,
+                               const float* d_normals, const uint16_t* d_attributes, uint8_t* d_facets);
 TB200_API int tb200_triangle_normals(tb200_ctx* ctx, const float* d_vertices, const uint32_t* d_triangles, uint32_t ntriangles,
                                      float* d_normals);
 

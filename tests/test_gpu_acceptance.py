@@ -96,6 +96,15 @@ def test_reference_clients_against_our_library():
         return np.ascontiguousarray(rec[:, 12:48]).view(np.float32)          # the three vertices of every facet
     a, b = tris(os.path.join(out, "data", "StanfordBunny.stl")), tris(os.path.join(out, "bunny_test_out.stl"))
     assert a.shape == b.shape and np.array_equal(a, b)
+    # the same two tools linked WITHOUT the reference's iostl.c: the STL is read, de-duplicated and written by
+    # our library (include/trico_b200_io.h) - same archive, same STL, byte for byte
+    if os.path.exists(os.path.join(out, "trico_encoder_gpuio")):
+        for cmd in (["./trico_encoder_gpuio", "-i", "data/StanfordBunny.stl", "-o", "bunny_gpuio.trc"],
+                    ["./trico_decoder_gpuio", "-i", "bunny_gpuio.trc", "-o", "bunny_gpuio_out.stl"]):
+            r = subprocess.run(cmd, cwd=out, env=env, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, (cmd, r.stdout[-500:], r.stderr[-500:])
+        assert open(os.path.join(out, "bunny_gpuio.trc"), "rb").read() == open(os.path.join(out, "bunny_test.trc"), "rb").read()
+        assert open(os.path.join(out, "bunny_gpuio_out.stl"), "rb").read() == open(os.path.join(out, "bunny_test_out.stl"), "rb").read()
     # the same unmodified encoder, told through the environment to write the reference's own format:
     # the compiled reference library reads the archive the GPU wrote
     env0 = dict(env); env0["TRICO_B200_FORMAT"] = "0"

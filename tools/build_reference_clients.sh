@@ -25,5 +25,10 @@ AUX=("$OUT/iostl.o" "$OUT/ioply.o" "$OUT/rply.o" "$OUT/lz4.o")
 LINK=(-L"$LIBDIR" -ltrico_b200 -Wl,-rpath,"$LIBDIR" -lm)
 gcc "${CFLAGS[@]}" "${INC[@]}" "$REF/tools/trico_encoder/main.c" "${AUX[@]}" -o "$OUT/trico_encoder" "${LINK[@]}"
 gcc "${CFLAGS[@]}" "${INC[@]}" "$REF/tools/trico_decoder/main.c" "${AUX[@]}" -o "$OUT/trico_decoder" "${LINK[@]}"
+# the same two tools with the STL front-end taken from OUR library as well (trico_read_stl, trico_read_stl_full,
+# trico_write_stl: include/trico_b200_io.h) - the reference's iostl.c is simply left out of the link
+AUX_GPUIO=("$OUT/ioply.o" "$OUT/rply.o" "$OUT/lz4.o")
+gcc "${CFLAGS[@]}" "${INC[@]}" "$REF/tools/trico_encoder/main.c" "${AUX_GPUIO[@]}" -o "$OUT/trico_encoder_gpuio" "${LINK[@]}"
+gcc "${CFLAGS[@]}" "${INC[@]}" "$REF/tools/trico_decoder/main.c" "${AUX_GPUIO[@]}" -o "$OUT/trico_decoder_gpuio" "${LINK[@]}"
 g++ -std=c++17 "${CFLAGS[@]}" "${INC[@]}" -I"$REF/trico.tests" "$REF"/trico.tests/*.cpp "${AUX[@]}" -o "$OUT/trico.tests" "${LINK[@]}"
 echo "built: $OUT/trico_encoder $OUT/trico_decoder $OUT/trico.tests"

@@ -94,6 +94,8 @@ def load() -> C.CDLL:
         "tb200_stl_dedup_scratch_bytes": (C.c_uint64, [C.c_uint32]),
         "tb200_stl_last_sort_passes": (C.c_int, []),
         "tb200_triangle_normals": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp]),
+        "tb200_stl_facets": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp]),
+        "trico_write_stl": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_char_p]),
         "trico_b200_triangle_normals": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _vp]),
         "trico_read_stl": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(_vp), C.POINTER(C.c_uint32), C.POINTER(_vp), C.c_char_p]),
         "trico_read_stl_full": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(_vp), C.POINTER(C.c_uint32), C.POINTER(_vp),

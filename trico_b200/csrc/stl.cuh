@@ -302,4 +302,29 @@ triangle_normals_kernel(const float* __restrict__ vertices, const uint32_t* __re
   normals[(size_t)t * 3 + 2] = nz_len ? __fdiv_rn(nz, len) : nz;
   }
 
+// ---------------------------------------------------------------------------------------------
+// indexed mesh -> the 50-byte facet records of a binary STL file (trico_write_stl, iostl.c:261-320):
+// normal (zeros when there are none), the three corner positions, the attribute word (zero when none)
+__global__ void __launch_bounds__(STL_THREADS)
+stl_facets_kernel(const float* __restrict__ vertices, const uint32_t* __restrict__ triangles, uint32_t ntri,
+                  const float* __restrict__ normals, const uint16_t* __restrict__ attrs, uint8_t* __restrict__ out)
+  {
+  const uint32_t t = blockIdx.x * STL_THREADS + threadIdx.x;
+  if (t >= ntri) return;
+  uint32_t w[12];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) w[i] = normals ? __float_as_uint(normals[(size_t)t * 3 + i]) : 0u;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    {
+    const uint32_t v = triangles[(size_t)t * 3 + j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[3 + 3 * j + i] = __float_as_uint(vertices[(size_t)v * 3 + i]);
+    }
+  uint16_t* q = reinterpret_cast<uint16_t*>(out + (size_t)t * STL_FACET_BYTES);      // 50 t: 2-byte aligned
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { q[2 * i] = (uint16_t)w[i]; q[2 * i + 1] = (uint16_t)(w[i] >> 16); }
+  q[24] = attrs ? attrs[t] : (uint16_t)0;
+  }
+
 }  // namespace tb200
