@@ -913,6 +913,69 @@ constexpr int LZ4_ASM_THREADS = 256;
 constexpr int LZ4_ASM_TILE = 128;           // 64 measured the same, 256 slower
 
 #ifndef TB200_HOST_EMU
+#ifndef TB200_LZ4_ASM_BIG
+#define TB200_LZ4_ASM_BIG 4096
+#endif
+constexpr uint32_t LZ4_ASM_BIG = TB200_LZ4_ASM_BIG;   // blocks from this size on are copied by the whole CTA
+
+// nbytes from src (16-byte aligned, one readable spare vector behind the block) to dst (any alignment) by NT
+// threads, tid = 0..NT-1
+template <int NT>
+__device__ __forceinline__ void lz4_asm_copy(uint8_t* dst, const uint8_t* src, uint32_t nbytes, uint32_t tid)
+  {
+  uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+  if (head > nbytes) head = nbytes;
+  const uint32_t nvec = (nbytes - head) >> 4;
+  const uint32_t done = head + (nvec << 4);
+  uint8_t hb = 0, tb = 0;
+  if (tid < head) hb = __ldcs(src + tid);
+  if (done + tid < nbytes) tb = __ldcs(src + done + tid);
+  uint4* dv = reinterpret_cast<uint4*>(dst + head);
+  const uint4* sv = reinterpret_cast<const uint4*>(src);                      // vector i of the body = source bytes [head + 16 i, head + 16 i + 16)
+  const unsigned sh = (head & 3u) * 8u;
+  const uint32_t ws = head >> 2;                                              // 0..3, the same for the whole block
+  constexpr int UN = 4;
+  for (uint32_t i0 = tid; i0 < nvec; i0 += NT * UN)
+    {
+    uint4 va[UN], vb[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      {
+      const uint32_t i = i0 + (uint32_t)u * NT;
+      if (i < nvec) { va[u] = __ldcs(sv + i); if (head) vb[u] = __ldcs(sv + i + 1); }
+      }
+    if (i0 == tid)
+      { // (the first batch's loads are under way)
+      if (tid < head) dst[tid] = hb;
+      if (done + tid < nbytes) dst[done + tid] = tb;
+      }
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      {
+      const uint32_t i = i0 + (uint32_t)u * NT;
+      if (i >= nvec) continue;
+      uint4 o = va[u];
+      if (head)
+        {
+        const uint32_t w[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+        switch (ws)
+          {
+          case 0: o = make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh)); break;
+          case 1: o = make_uint4(__funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh)); break;
+          case 2: o = make_uint4(__funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh)); break;
+          default: o = make_uint4(__funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh), __funnelshift_r(w[6], w[7], sh)); break;
+          }
+        }
+      dv[i] = o;
+      }
+    }
+  if (tid >= nvec)
+    { // threads that had no vector of the first batch
+    if (tid < head) dst[tid] = hb;
+    if (done + tid < nbytes) dst[done + tid] = tb;
+    }
+  }
+
 __global__ void __launch_bounds__(LZ4_ASM_THREADS)
 lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks, const Lz4StreamHeader h)
   {
@@ -968,66 +1031,25 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks, const Lz4StreamHead
     }
   __syncthreads();
   // Large blocks (an incompressible plane is 200 times larger than a constant one) are copied by the
-  // whole CTA, one after the other: 16-byte stores to the aligned body of the destination, each
-  // built from the two aligned source vectors around it (the shift is the same for the whole
-  // block).  Small blocks take one warp each, byte by byte.
+  // whole CTA, one after the other; every smaller block takes one warp, eight blocks in flight per CTA.
+  // Either way (lz4_asm_copy): 16-byte stores to the aligned body of the destination, each built from
+  // the two aligned source vectors around it (the shift is the same for the whole block), and EVERY
+  // load of a batch - head bytes, tail bytes, vectors - is issued before the first store: a block of a
+  // few hundred bytes costs one memory latency, not one per 32 bytes.
   const uint32_t nloc = (uint32_t)((nchunks - g0 < (uint64_t)LZ4_ASM_TILE) ? (nchunks - g0) : (uint64_t)LZ4_ASM_TILE);
   uint8_t* D = a.payload + sh_base;
   const uint8_t* sbase = a.scratch + g0 * a.slot;
-  constexpr uint32_t BIG = 512;
   for (uint32_t c = 0; c < nloc; ++c)
     {
     const uint32_t nbytes = sh_sz[c];
-    if (nbytes < BIG) continue;
-    const uint8_t* src = sbase + (size_t)c * a.slot;                           // 16-byte aligned, one spare vector behind every block
-    uint8_t* dst = D + sh_off[c];
-    const uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
-    if (threadIdx.x < head) dst[threadIdx.x] = __ldcs(src + threadIdx.x);
-    const uint32_t nvec = (nbytes - head) >> 4;
-    uint4* dv = reinterpret_cast<uint4*>(dst + head);
-    const uint4* sv = reinterpret_cast<const uint4*>(src);                      // vector i of the body = source bytes [head + 16 i, head + 16 i + 16)
-    const unsigned sh = (head & 3u) * 8u;
-    const uint32_t ws = head >> 2;                                              // 0..3, the same for the whole block
-    constexpr int UN = 4;
-    for (uint32_t i0 = threadIdx.x; i0 < nvec; i0 += LZ4_ASM_THREADS * UN)
-      {
-      uint4 va[UN], vb[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u)
-        {
-        const uint32_t i = i0 + (uint32_t)u * LZ4_ASM_THREADS;
-        if (i < nvec) { va[u] = __ldcs(sv + i); if (head) vb[u] = __ldcs(sv + i + 1); }
-        }
-#pragma unroll
-      for (int u = 0; u < UN; ++u)
-        {
-        const uint32_t i = i0 + (uint32_t)u * LZ4_ASM_THREADS;
-        if (i >= nvec) continue;
-        uint4 o = va[u];
-        if (head)
-          {
-          const uint32_t w[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-          switch (ws)
-            {
-            case 0: o = make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh)); break;
-            case 1: o = make_uint4(__funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh)); break;
-            case 2: o = make_uint4(__funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh)); break;
-            default: o = make_uint4(__funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh), __funnelshift_r(w[6], w[7], sh)); break;
-            }
-          }
-        dv[i] = o;
-        }
-      }
-    const uint32_t done = head + (nvec << 4);
-    if (done + threadIdx.x < nbytes) dst[done + threadIdx.x] = __ldcs(src + done + threadIdx.x);
+    if (nbytes < LZ4_ASM_BIG) continue;
+    lz4_asm_copy<LZ4_ASM_THREADS>(D + sh_off[c], sbase + (size_t)c * a.slot, nbytes, threadIdx.x);
     }
   for (uint32_t c = warp; c < nloc; c += LZ4_ASM_THREADS / 32)
     {
     const uint32_t nbytes = sh_sz[c];
-    if (nbytes >= BIG) continue;
-    const uint8_t* src = sbase + (size_t)c * a.slot;
-    uint8_t* dst = D + sh_off[c];
-    for (uint32_t i = lane; i < nbytes; i += 32) dst[i] = __ldcs(src + i);
+    if (nbytes >= LZ4_ASM_BIG || nbytes == 0) continue;
+    lz4_asm_copy<32>(D + sh_off[c], sbase + (size_t)c * a.slot, nbytes, lane);
     }
   }
 
