@@ -218,6 +218,23 @@ static int set_smem(K kernel, size_t bytes, const tb200_ctx* c)
   return 1;
   }
 
+// the assembly kernel of the LZ4 path (and of small FPC streams): streams whose blocks can be large get a ring
+// of shared-memory stages, one scratch slot each, that bulk copies (TMA) fill ahead of the CTA
+static int launch_lz4_assemble(tb200_ctx* c, const Lz4EncodeArgs& a, uint64_t nchunks, unsigned ntiles)
+  {
+  Lz4StreamHeader h = take_header();
+  size_t smem = 0;
+  static const int use_ring = getenv("TB200_LZ4_ASM_NO_RING") ? 0 : 1;
+  if (use_ring && a.slot >= LZ4_ASM_BIG && (a.slot & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.scratch) & 15u) == 0)
+    {
+    h.stages = (size_t)a.slot * 4 <= (72u << 10) ? 4u : ((size_t)a.slot * 2 <= (72u << 10) ? 2u : 0u);
+    smem = (size_t)h.stages * a.slot;
+    if (smem && !set_smem(lz4_assemble_kernel, smem, c)) return 0;
+    }
+  lz4_assemble_kernel<<<ntiles, LZ4_ASM_THREADS, smem, c->stream>>>(a, nchunks, h);
+  return 1;
+  }
+
 // resident CTAs per SM and SM count for a persistent grid
 template <typename K>
 static int persistent_grid(K kernel, int threads, size_t smem, const tb200_ctx* c, int* per_sm, int* sms)
@@ -375,7 +392,7 @@ static int launch_fpc_encode_small(tb200_ctx* c, const FpcEncodeArgs& f, int wor
     if (!set_smem(fpc_encode_chunks_kernel<uint64_t>, smem, c)) return 0;
     fpc_encode_chunks_kernel<uint64_t><<<grid, FPC_CHUNKS_WARPS * 32, smem, c->stream>>>(k);
     }
-  lz4_assemble_kernel<<<ntiles, LZ4_ASM_THREADS, 0, c->stream>>>(a, nchunks, take_header());
+  if (!launch_lz4_assemble(c, a, nchunks, ntiles)) return 0;
   c->launches += 2;
   CK(cudaGetLastError());
   return 1;

@@ -732,6 +732,7 @@ struct Lz4StreamHeader
   uint32_t hdr_count = 0;
   uint8_t hdr_type = 0, hdr_info = 0, hdr_log2 = 0;
   uint64_t hdr_fixed_plus_table = 0;
+  uint32_t stages = 0;             // assembly: shared-memory stages of `slot` bytes for the bulk-copy ring (0: register path)
   };
 
 constexpr int LZ4_HLOG = 10;     // default: 1024 u16 entries = 2 KiB per warp (12 resident warps per SM with 16 KiB blocks)
@@ -920,6 +921,38 @@ constexpr uint32_t LZ4_ASM_BIG = TB200_LZ4_ASM_BIG;   // blocks from this size o
 
 // nbytes from src (16-byte aligned, one readable spare vector behind the block) to dst (any alignment) by NT
 // threads, tid = 0..NT-1
+// destination vector = 16 source bytes starting `4 ws + sh / 8` bytes into the aligned pair (va, vb)
+__device__ __forceinline__ uint4 lz4_asm_shift(const uint4 va, const uint4 vb, uint32_t ws, unsigned sh)
+  {
+  const uint32_t w[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+  switch (ws)
+    {
+    case 0: return make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh));
+    case 1: return make_uint4(__funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh));
+    case 2: return make_uint4(__funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh));
+    default: return make_uint4(__funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh), __funnelshift_r(w[6], w[7], sh));
+    }
+  }
+
+// the same copy out of a shared-memory stage (16-byte aligned, filled by a bulk copy), whole CTA
+__device__ __forceinline__ void lz4_asm_copy_staged(uint8_t* dst, const uint8_t* stage, uint32_t nbytes, uint32_t tid, uint32_t nthreads)
+  {
+  uint32_t head = (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u);
+  if (head > nbytes) head = nbytes;
+  const uint32_t nvec = (nbytes - head) >> 4;
+  const uint32_t done = head + (nvec << 4);
+  if (tid < head) dst[tid] = stage[tid];
+  if (done + tid < nbytes) dst[done + tid] = stage[done + tid];
+  uint4* dv = reinterpret_cast<uint4*>(dst + head);
+  const uint4* sv = reinterpret_cast<const uint4*>(stage);
+  const unsigned sh = (head & 3u) * 8u;
+  const uint32_t ws = head >> 2;
+  if (head)
+    for (uint32_t i = tid; i < nvec; i += nthreads) __stcs(dv + i, lz4_asm_shift(sv[i], sv[i + 1], ws, sh));
+  else
+    for (uint32_t i = tid; i < nvec; i += nthreads) __stcs(dv + i, sv[i]);
+  }
+
 template <int NT>
 __device__ __forceinline__ void lz4_asm_copy(uint8_t* dst, const uint8_t* src, uint32_t nbytes, uint32_t tid)
   {
@@ -954,19 +987,7 @@ __device__ __forceinline__ void lz4_asm_copy(uint8_t* dst, const uint8_t* src, u
       {
       const uint32_t i = i0 + (uint32_t)u * NT;
       if (i >= nvec) continue;
-      uint4 o = va[u];
-      if (head)
-        {
-        const uint32_t w[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-        switch (ws)
-          {
-          case 0: o = make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh)); break;
-          case 1: o = make_uint4(__funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh)); break;
-          case 2: o = make_uint4(__funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh)); break;
-          default: o = make_uint4(__funnelshift_r(w[3], w[4], sh), __funnelshift_r(w[4], w[5], sh), __funnelshift_r(w[5], w[6], sh), __funnelshift_r(w[6], w[7], sh)); break;
-          }
-        }
-      dv[i] = o;
+      dv[i] = head ? lz4_asm_shift(va[u], vb[u], ws, sh) : va[u];
       }
     }
   if (tid >= nvec)
@@ -1039,17 +1060,73 @@ lz4_assemble_kernel(const Lz4EncodeArgs a, uint64_t nchunks, const Lz4StreamHead
   const uint32_t nloc = (uint32_t)((nchunks - g0 < (uint64_t)LZ4_ASM_TILE) ? (nchunks - g0) : (uint64_t)LZ4_ASM_TILE);
   uint8_t* D = a.payload + sh_base;
   const uint8_t* sbase = a.scratch + g0 * a.slot;
-  for (uint32_t c = 0; c < nloc; ++c)
+  // With a stage ring (h.stages > 0) the large blocks arrive by bulk copy (TMA, one instruction of one
+  // thread per block), `stages` blocks ahead of the CTA: the bytes in flight per SM are bounded by
+  // shared memory (3 CTAs x 4 x 16.5 KB) instead of by registers (4 CTAs x 256 threads x 8 vectors), and
+  // the small blocks' latencies pass while the first stages fill.
+  // (16, like every other kernel's dynamic shared memory: all `extern __shared__` arrays of a translation unit
+  // are ONE symbol, and a larger alignment here moves the dynamic base of every other kernel - measured: it
+  // pads lz4_decode_multi_kernel's static shared memory from 1360 to 1408 bytes and that kernel then faults)
+  extern __shared__ __align__(16) uint8_t asm_stage[];
+  __shared__ uint8_t sh_big[LZ4_ASM_TILE];
+  __shared__ uint32_t sh_nbig;
+  __shared__ __align__(8) uint64_t sh_full[4];
+  const uint32_t stages = h.stages;
+  uint64_t pol_first = 0;
+  if (stages)
     {
-    const uint32_t nbytes = sh_sz[c];
-    if (nbytes < LZ4_ASM_BIG) continue;
-    lz4_asm_copy<LZ4_ASM_THREADS>(D + sh_off[c], sbase + (size_t)c * a.slot, nbytes, threadIdx.x);
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+    if (warp == 0)
+      {
+      uint32_t n = 0;
+      for (uint32_t c0 = 0; c0 < nloc; c0 += 32)
+        {
+        const uint32_t c = c0 + lane;
+        const bool big = c < nloc && sh_sz[c] >= LZ4_ASM_BIG;
+        const unsigned m = __ballot_sync(FULL, big);
+        if (big) sh_big[n + __popc(m & lanemask_lt())] = (uint8_t)c;
+        n += __popc(m);
+        }
+      if (lane == 0)
+        {
+        sh_nbig = n;
+        for (uint32_t st = 0; st < stages; ++st) mbar_init((uint32_t)__cvta_generic_to_shared(&sh_full[st]), 1);
+        }
+      }
+    __syncthreads();
     }
+  const uint32_t nbig = stages ? sh_nbig : 0;
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(asm_stage);
+  auto issue = [&](uint32_t j)
+    { // one thread: block j of the list -> its stage
+    const uint32_t c = sh_big[j], st = j % stages;
+    const uint32_t nb16 = (sh_sz[c] + 15u) & ~15u;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sh_full[st]);
+    mbar_expect_tx(bar, nb16);
+    bulk_g2s(stage_s + st * a.slot, sbase + (size_t)c * a.slot, nb16, bar, pol_first);
+    };
+  if (stages && threadIdx.x == 0)
+    for (uint32_t j = 0; j < stages && j < nbig; ++j) issue(j);
+  if (!stages)
+    for (uint32_t c = 0; c < nloc; ++c)
+      {
+      const uint32_t nbytes = sh_sz[c];
+      if (nbytes < LZ4_ASM_BIG) continue;
+      lz4_asm_copy<LZ4_ASM_THREADS>(D + sh_off[c], sbase + (size_t)c * a.slot, nbytes, threadIdx.x);
+      }
   for (uint32_t c = warp; c < nloc; c += LZ4_ASM_THREADS / 32)
     {
     const uint32_t nbytes = sh_sz[c];
     if (nbytes >= LZ4_ASM_BIG || nbytes == 0) continue;
     lz4_asm_copy<32>(D + sh_off[c], sbase + (size_t)c * a.slot, nbytes, lane);
+    }
+  for (uint32_t j = 0; j < nbig; ++j)
+    {
+    const uint32_t c = sh_big[j], st = j % stages;
+    mbar_wait((uint32_t)__cvta_generic_to_shared(&sh_full[st]), (j / stages) & 1u);
+    lz4_asm_copy_staged(D + sh_off[c], asm_stage + (size_t)st * a.slot, sh_sz[c], threadIdx.x, LZ4_ASM_THREADS);
+    __syncthreads();                                        // the stage has been read by everybody
+    if (threadIdx.x == 0 && j + stages < nbig) issue(j + stages);
     }
   }
 
