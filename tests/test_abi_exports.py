@@ -66,3 +66,29 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".c", ".cu", ".cuh", ".inc", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.replace("the CPU oracle", "").lower() or f in ("build.py",), (dirpath, f)
+
+
+def test_dynamic_shared_memory_is_declared_alike_everywhere():
+    """All `extern __shared__` arrays of the one CUDA translation unit are ONE symbol: a larger alignment on any
+    of them moves the dynamic shared memory of every kernel ("A shared-memory hazard")."""
+    csrc = os.path.join(ROOT, "trico_b200", "csrc")
+    seen = []
+    for f in sorted(os.listdir(csrc)):
+        text = open(os.path.join(csrc, f), errors="ignore").read()
+        seen += [(f, m) for m in re.findall(r"extern\s+__shared__\s+(?:__align__\((\w+)\))?", text)]
+    assert len(seen) >= 10
+    assert all(a == "16" for _, a in seen), seen
+
+
+def test_library_carries_tma_bulk_copies():
+    """the float encoder's slab staging and the assembly's stage ring are cp.async.bulk + mbarrier: UBLKCP / SYNCS in SASS"""
+    import shutil
+    import subprocess
+    import trico_b200
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    trico_b200.load()
+    sass = subprocess.run([tool, "-sass", trico_b200.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    assert sass.count("UBLKCP") >= 32 and "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK" in sass
