@@ -92,3 +92,29 @@ def test_library_carries_tma_bulk_copies():
     trico_b200.load()
     sass = subprocess.run([tool, "-sass", trico_b200.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
     assert sass.count("UBLKCP") >= 32 and "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK" in sass
+
+
+def test_stl_front_end_without_a_gpu(tmp_path):
+    """include/trico_b200_io.h: the refusals of the reference's reader need no device; a real file fails loudly
+    without one (no CPU de-duplication hides behind the API)."""
+    import numpy as np
+    import trico_b200
+    sys_path_oracle = os.path.join(ROOT, "oracle")
+    import sys
+    sys.path.insert(0, sys_path_oracle)
+    from checkers import c_read_stl, stl_facets, stl_file_bytes
+    lib = trico_b200.load()
+    assert lib.tb200_stl_dedup_scratch_bytes(0) > 0
+    assert lib.tb200_stl_dedup_scratch_bytes(1000000) >= 2 * 16 * 3000000 + 4 * 3000000      # two record arrays + the flags
+    assert c_read_stl(trico_b200.LIB_PATH, os.path.join(tmp_path, "missing.stl")) is None
+    open(os.path.join(tmp_path, "ascii.stl"), "wb").write(b"solid x\n" + b" " * 200)
+    assert c_read_stl(trico_b200.LIB_PATH, os.path.join(tmp_path, "ascii.stl")) is None           # iostl.c:157-161
+    open(os.path.join(tmp_path, "empty.stl"), "wb").write(stl_file_bytes(np.zeros((0, 50), np.uint8)))
+    ev, et = c_read_stl(trico_b200.LIB_PATH, os.path.join(tmp_path, "empty.stl"))                # iostl.c:72-73: nothing to do
+    assert ev.shape[0] == 0 and et.shape[0] == 0
+    if lib.tb200_device_count() > 0:
+        return
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    open(os.path.join(tmp_path, "one.stl"), "wb").write(stl_file_bytes(stl_facets(v, np.array([[0, 1, 2]], np.uint32))))
+    assert c_read_stl(trico_b200.LIB_PATH, os.path.join(tmp_path, "one.stl")) is None
+    assert lib.tb200_last_error()
